@@ -1,0 +1,68 @@
+"""Build recipe for librt_b200.so (the C-ABI library: CUDA kernels for sm_100a + host lowering).
+
+Everything is compiled in-tree with nvcc; the .so is git-ignored but travels to the GPU box.
+  -gencode arch=compute_100a,code=sm_100a   B200 only, no PTX for other targets
+  -fmad=false                               no implicit FMA contraction: the intersection math must be
+                                            the reference's sequence of single IEEE operations
+                                            (explicit __fmaf_rn is used where exactness is not needed)
+  -Xcompiler -ffp-contract=off              same for the host lowering (precomputed records)
+"""
+from __future__ import annotations
+
+import os
+import shutil
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+LIB = os.path.join(HERE, "librt_b200.so")
+SOURCES = ["rt_kernels.cu", "rt_api.cu", "rt_lower.cpp"]
+HEADERS = ["rt_kernels.h", "rt_lower.h", "rt_types.h", os.path.join("..", "..", "include", "rt_b200.h")]
+
+
+def _nvcc() -> str:
+    for cand in (os.environ.get("NVCC"), shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
+        if cand and os.path.exists(cand):
+            return cand
+    raise RuntimeError("nvcc not found")
+
+
+def _host_cxx() -> list[str]:
+    # the image's $CXX wrapper lacks some spec files; the system g++ is the safe host compiler
+    return ["-ccbin", "/usr/bin/g++"] if os.path.exists("/usr/bin/g++") else []
+
+
+def needs_build() -> bool:
+    if not os.path.exists(LIB):
+        return True
+    t = os.path.getmtime(LIB)
+    deps = [os.path.join(CSRC, f) for f in SOURCES + HEADERS] + [os.path.abspath(__file__)]
+    return any(os.path.getmtime(d) > t for d in deps)
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    if not force and not needs_build():
+        return LIB
+    cmd = [
+        _nvcc(), *_host_cxx(),
+        "-gencode", "arch=compute_100a,code=sm_100a",
+        "-lineinfo", "-O3", "-std=c++17",
+        "-fmad=false",
+        "-Xcompiler", "-fPIC,-ffp-contract=off,-fno-fast-math,-O3",
+        "-shared", "-o", LIB,
+        *[os.path.join(CSRC, f) for f in SOURCES],
+    ]
+    if verbose:
+        cmd.insert(1, "-Xptxas=-v")
+        print(" ".join(cmd), file=sys.stderr)
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("nvcc failed:\n" + r.stdout + r.stderr)
+    if verbose:
+        print(r.stderr, file=sys.stderr)
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose=True))

@@ -1,0 +1,799 @@
+// rt_api.cu — implementation of the C ABI in include/rt_b200.h: scene IR, commit (lower +
+// upload), the host side of the wavefront loop, resolve, parity hooks, asset readers.
+// There is deliberately no CPU rendering path in this library: every device entry point fails
+// with RT_ERR_CUDA when no CUDA device is usable.
+
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "rt_kernels.h"
+#include "rt_lower.h"
+
+namespace {
+thread_local std::string g_err;
+int fail(int code, const std::string& msg) {
+  g_err = msg;
+  return code;
+}
+#define CUDA_TRY(expr)                                                                        \
+  do {                                                                                        \
+    cudaError_t e_ = (expr);                                                                  \
+    if (e_ != cudaSuccess) return fail(RT_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e_)); \
+  } while (0)
+
+struct DevBuf {
+  void* p = nullptr;
+  size_t bytes = 0;
+};
+}  // namespace
+
+struct rt_scene {
+  std::vector<rt::HostTexture> textures;
+  std::vector<rt_material_desc> materials;
+  std::vector<rt::HostMesh> meshes;
+  std::vector<rt::HostObject> objects;
+  int n_volumes = 0;
+
+  // lowered (host) + resident (device)
+  rt::Lowered low;
+  bool lowered = false;
+  bool committed = false;
+  int device = -1;
+  DevBuf d_nodes, d_tris, d_shade, d_objects, d_mats, d_textures, d_texels, d_planes;
+  rt_dev_scene dev{};
+
+  // wavefront state
+  uint32_t capacity = 0;
+  rt::rt_paths paths[2] = {};
+  rt::rt_hits hits = {};
+  uint32_t* queues = nullptr;
+  rt_ctrl* ctrl = nullptr;
+  rt_ctrl* h_ctrl = nullptr;     // pinned
+  uint32_t* h_done = nullptr;    // pinned poll slots
+  cudaEvent_t poll_ev[2] = {nullptr, nullptr};
+  std::vector<cudaEvent_t> events;
+  cudaStream_t own_stream = nullptr;
+  // scratch for host-buffer entry points
+  DevBuf d_accum, d_linear, d_rgb8, d_dbg;
+};
+
+namespace {
+
+void free_buf(DevBuf& b) {
+  if (b.p) cudaFree(b.p);
+  b.p = nullptr;
+  b.bytes = 0;
+}
+int ensure_buf(DevBuf& b, size_t bytes) {
+  if (b.bytes >= bytes && b.p) return RT_OK;
+  free_buf(b);
+  CUDA_TRY(cudaMalloc(&b.p, std::max<size_t>(bytes, 16)));
+  b.bytes = std::max<size_t>(bytes, 16);
+  return RT_OK;
+}
+int upload(DevBuf& b, const void* src, size_t bytes, cudaStream_t st) {
+  int rc = ensure_buf(b, bytes);
+  if (rc != RT_OK) return rc;
+  if (bytes) CUDA_TRY(cudaMemcpyAsync(b.p, src, bytes, cudaMemcpyHostToDevice, st));
+  return RT_OK;
+}
+
+void free_wavefront(rt_scene* s) {
+  for (int k = 0; k < 2; ++k) {
+    if (s->paths[k].A) cudaFree(s->paths[k].A);
+    if (s->paths[k].B) cudaFree(s->paths[k].B);
+    if (s->paths[k].C) cudaFree(s->paths[k].C);
+    s->paths[k] = rt::rt_paths{};
+  }
+  if (s->hits.H0) cudaFree(s->hits.H0);
+  if (s->hits.H1) cudaFree(s->hits.H1);
+  if (s->hits.H2) cudaFree(s->hits.H2);
+  s->hits = rt::rt_hits{};
+  if (s->queues) cudaFree(s->queues);
+  s->queues = nullptr;
+  s->capacity = 0;
+}
+
+int ensure_wavefront(rt_scene* s, uint32_t capacity) {
+  if (!s->ctrl) {
+    CUDA_TRY(cudaMalloc((void**)&s->ctrl, sizeof(rt_ctrl)));
+    CUDA_TRY(cudaMallocHost((void**)&s->h_ctrl, sizeof(rt_ctrl)));
+    CUDA_TRY(cudaMallocHost((void**)&s->h_done, 2 * sizeof(uint32_t)));
+    CUDA_TRY(cudaEventCreateWithFlags(&s->poll_ev[0], cudaEventDisableTiming));
+    CUDA_TRY(cudaEventCreateWithFlags(&s->poll_ev[1], cudaEventDisableTiming));
+    CUDA_TRY(cudaStreamCreateWithFlags(&s->own_stream, cudaStreamNonBlocking));
+  }
+  if (s->capacity >= capacity && s->queues) return RT_OK;
+  free_wavefront(s);
+  size_t n = capacity;
+  for (int k = 0; k < 2; ++k) {
+    CUDA_TRY(cudaMalloc((void**)&s->paths[k].A, n * 16));
+    CUDA_TRY(cudaMalloc((void**)&s->paths[k].B, n * 16));
+    CUDA_TRY(cudaMalloc((void**)&s->paths[k].C, n * 16));
+  }
+  CUDA_TRY(cudaMalloc((void**)&s->hits.H0, n * 16));
+  CUDA_TRY(cudaMalloc((void**)&s->hits.H1, n * 16));
+  CUDA_TRY(cudaMalloc((void**)&s->hits.H2, n * 4));
+  CUDA_TRY(cudaMalloc((void**)&s->queues, n * 4 * RT_NUM_CLASSES));
+  s->capacity = capacity;
+  return RT_OK;
+}
+
+int check_camera(const rt_camera* cam) {
+  if (!cam) return fail(RT_ERR_INVALID, "camera is NULL");
+  if (cam->projection_mode != RT_PROJ_PERSPECTIVE)
+    return fail(RT_ERR_UNSUPPORTED, "only CameraProjectionMode::Perspective is on the GPU path (tracing.rs:196-201)");
+  if (cam->shading_mode != RT_SHADE_PATHTRACE)
+    return fail(RT_ERR_UNSUPPORTED, "only ShadingMode::PathTrace is on the GPU path (tracing.rs:276)");
+  if (cam->path_samples != 1) return fail(RT_ERR_UNSUPPORTED, "path_samples must be 1 (tracing.rs:146,370)");
+  if (cam->screen_width == 0 || cam->screen_height == 0) return fail(RT_ERR_INVALID, "empty image");
+  if ((uint64_t)cam->screen_width * cam->screen_height > (1ull << 31)) return fail(RT_ERR_INVALID, "image too large");
+  if (cam->aa_sample_count == 0 || cam->aa_sample_count >= (1u << 24))
+    return fail(RT_ERR_INVALID, "aa_sample_count must be in [1, 2^24)");
+  if (cam->path_depth >= 256) return fail(RT_ERR_INVALID, "path_depth must be < 256");
+  if ((uint32_t)std::sqrt((float)cam->aa_sample_count) == 0) return fail(RT_ERR_INVALID, "bad aa_sample_count");
+  return RT_OK;
+}
+
+// camera constants exactly as Camera::generate_rays computes them per sample (tracing.rs:160-191)
+void fill_frame_camera(const rt_camera& cam, uint64_t seed, rt_frame& fr) {
+  std::memset(&fr, 0, sizeof fr);
+  for (int k = 0; k < 3; ++k) fr.eye[k] = cam.eyepoint[k];
+  const float* v = cam.view_dir;
+  const float* u = cam.up;
+  float cx = v[1] * u[2] - v[2] * u[1], cy = v[2] * u[0] - v[0] * u[2], cz = v[0] * u[1] - v[1] * u[0];
+  float inv = 1.0f / std::sqrt(cx * cx + cy * cy + cz * cz);
+  fr.rot0[0] = cx * inv; fr.rot0[1] = cy * inv; fr.rot0[2] = cz * inv;
+  for (int k = 0; k < 3; ++k) {
+    fr.rot1[k] = u[k];
+    fr.rot2[k] = -v[k];
+  }
+  fr.pixel_size = 1.0f / (float)cam.screen_height;
+  fr.n = (float)cam.aa_sample_count;
+  fr.rootn = std::sqrt(fr.n);
+  fr.rooti = (uint32_t)fr.rootn;
+  fr.focal_length = cam.focal_length;
+  fr.focus_dist = cam.focus_dist;
+  fr.lens_radius = cam.lens_radius;
+  fr.t_min = 0.001f;  // tracing.rs:305
+  fr.t_max = cam.max_trace_dist;
+  fr.spp = cam.aa_sample_count;
+  fr.width = cam.screen_width;
+  fr.height = cam.screen_height;
+  fr.path_depth = cam.path_depth;
+  fr.k0 = (uint32_t)seed;
+  fr.k1 = (uint32_t)(seed >> 32);
+  fr.shard_mode = RT_SHARD_ALL;
+  fr.shard_count = 1;
+  fr.sample_begin = 0;
+  fr.sample_count = cam.aa_sample_count;
+}
+
+// resolves the shard description into (pixel-slot count, sample range); returns work item count
+int plan_shard(const rt_camera& cam, const rt_render_opts& o, rt_frame& fr, unsigned long long& total) {
+  uint32_t spp = cam.aa_sample_count;
+  uint32_t count = o.shard_count ? o.shard_count : 1;
+  if (o.shard_rank >= count) return fail(RT_ERR_INVALID, "shard_rank >= shard_count");
+  uint32_t sb = o.sample_begin, se = o.sample_end;
+  if (sb == 0 && se == 0) se = spp;
+  if (se > spp || sb > se) return fail(RT_ERR_INVALID, "bad sample range");
+  unsigned long long npix = (unsigned long long)cam.screen_width * cam.screen_height;
+  fr.shard_mode = o.shard_mode;
+  fr.shard_rank = o.shard_rank;
+  fr.shard_count = count;
+  switch (o.shard_mode) {
+    case RT_SHARD_ALL:
+      break;
+    case RT_SHARD_SAMPLES: {
+      // contiguous sample ranges of [sb, se), as even as possible
+      uint32_t n = se - sb, base = n / count, rem = n % count;
+      uint32_t b = sb + o.shard_rank * base + std::min(o.shard_rank, rem);
+      uint32_t e = b + base + (o.shard_rank < rem ? 1u : 0u);
+      sb = b;
+      se = e;
+      fr.shard_mode = RT_SHARD_ALL;  // on the device this is just a sample range
+      break;
+    }
+    case RT_SHARD_TILES: {
+      uint32_t ts = o.tile_size ? o.tile_size : 64;
+      if (ts > 1024) return fail(RT_ERR_INVALID, "tile_size too large");
+      fr.tile_size = ts;
+      fr.tiles_x = (cam.screen_width + ts - 1) / ts;
+      fr.tiles_y = (cam.screen_height + ts - 1) / ts;
+      uint32_t ntiles = fr.tiles_x * fr.tiles_y;
+      uint32_t mine = ntiles > o.shard_rank ? (ntiles - o.shard_rank + count - 1) / count : 0;
+      npix = (unsigned long long)mine * ts * ts;  // slots; those outside the image are skipped
+      break;
+    }
+    default:
+      return fail(RT_ERR_INVALID, "unknown shard_mode");
+  }
+  fr.sample_begin = sb;
+  fr.sample_count = se - sb;
+  total = fr.sample_count ? npix * fr.sample_count : 0;
+  if (fr.sample_count == 0) fr.sample_count = 1;  // never divide by zero on the device
+  return RT_OK;
+}
+
+const uint32_t kDefaultWavefront = 1u << 21;
+
+uint32_t pick_capacity(unsigned long long total, uint32_t requested) {
+  unsigned long long cap = requested ? requested : kDefaultWavefront;
+  cap = std::min<unsigned long long>(cap, std::max<unsigned long long>(total, 1));
+  cap = (cap + 127) / 128 * 128;
+  return (uint32_t)std::min<unsigned long long>(cap, 1ull << 27);
+}
+
+int set_device(rt_scene* s) {
+  if (!s) return fail(RT_ERR_INVALID, "scene is NULL");
+  if (!s->committed) return fail(RT_ERR_NOT_COMMITTED, "rt_commit has not been called on this scene");
+  CUDA_TRY(cudaSetDevice(s->device));
+  return RT_OK;
+}
+
+// The wavefront loop.  Launches are asynchronous; the device decides how many rays each
+// iteration has.  The host only peeks at a `done` flag every few iterations, two polls deep, so
+// the stream never drains.
+int run_wavefront(rt_scene* s, const rt_frame& fr_in, unsigned long long total, long long* d_accum, bool count,
+                  bool debug, rt::rt_debug dbg, bool single_iteration, bool use_events, cudaStream_t st,
+                  rt_stats* stats) {
+  rt_frame fr = fr_in;
+  int rc = ensure_wavefront(s, fr.capacity);
+  if (rc != RT_OK) return rc;
+  fr.capacity = s->capacity >= fr.capacity ? fr.capacity : s->capacity;
+  const int kChunk = 8;
+  size_t ev_used = 0;
+  auto next_event = [&](cudaEvent_t& ev) -> int {
+    if (ev_used == s->events.size()) {
+      cudaEvent_t e;
+      CUDA_TRY(cudaEventCreate(&e));
+      s->events.push_back(e);
+    }
+    ev = s->events[ev_used++];
+    return RT_OK;
+  };
+  const size_t kMaxTimedIters = 1u << 15;
+  cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
+  if ((rc = next_event(ev_begin)) != RT_OK) return rc;
+  if ((rc = next_event(ev_end)) != RT_OK) return rc;
+  CUDA_TRY(cudaEventRecord(ev_begin, st));
+  rt::launch_init(s->ctrl, total, st);
+  uint64_t launches = 1, ext_launches = 0, shd_launches = 0;
+  s->h_done[0] = s->h_done[1] = 0;
+  int chunk = 0;
+  bool done = false;
+  size_t timed_iters = 0;
+  size_t ev_iter_base = ev_used;
+  unsigned long long max_iters = single_iteration ? 1 : ~0ull;
+  unsigned long long it = 0;
+  while (!done && it < max_iters) {
+    for (int k = 0; k < kChunk && it < max_iters; ++k, ++it) {
+      int cur = (int)(it & 1), nxt = cur ^ 1;
+      rt::launch_advance(s->ctrl, fr.capacity, st);
+      launches += 2;
+      bool timed = use_events && timed_iters < kMaxTimedIters;
+      cudaEvent_t e0 = nullptr, e1 = nullptr, e2 = nullptr;
+      if (timed) {
+        if ((rc = next_event(e0)) != RT_OK || (rc = next_event(e1)) != RT_OK || (rc = next_event(e2)) != RT_OK) return rc;
+        CUDA_TRY(cudaEventRecord(e0, st));
+      }
+      rt::launch_extend(s->dev, fr, s->ctrl, s->paths[cur], s->hits, s->queues, dbg, count, debug, st);
+      if (timed) CUDA_TRY(cudaEventRecord(e1, st));
+      ++launches; ++ext_launches;
+      if (!single_iteration) {
+        rt::launch_shade(s->dev, fr, s->ctrl, s->paths[cur], s->paths[nxt], s->hits, s->queues, d_accum, count, st);
+        ++launches; ++shd_launches;
+      }
+      if (timed) {
+        CUDA_TRY(cudaEventRecord(e2, st));
+        ++timed_iters;
+      }
+    }
+    if (single_iteration) break;
+    // poll: copy the done flag written by k_advance, two chunks deep
+    int slot = chunk & 1;
+    if (chunk >= 2) {
+      CUDA_TRY(cudaEventSynchronize(s->poll_ev[slot]));
+      if (s->h_done[slot]) done = true;
+    }
+    if (!done) {
+      CUDA_TRY(cudaMemcpyAsync(&s->h_done[slot], &s->ctrl->done, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+      CUDA_TRY(cudaEventRecord(s->poll_ev[slot], st));
+    }
+    ++chunk;
+  }
+  CUDA_TRY(cudaEventRecord(ev_end, st));
+  CUDA_TRY(cudaMemcpyAsync(s->h_ctrl, s->ctrl, sizeof(rt_ctrl), cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaStreamSynchronize(st));
+  CUDA_TRY(cudaGetLastError());
+  if (!single_iteration && !s->h_ctrl->done && s->h_ctrl->cursor != s->h_ctrl->total)
+    return fail(RT_ERR_CUDA, "wavefront loop ended before all work was issued");
+  if (stats) {
+    const rt_ctrl& c = *s->h_ctrl;
+    stats->samples += c.n_samples - c.counters[7];
+    stats->rays += c.n_rays_total - c.counters[7];
+    stats->iterations += c.iterations;
+    stats->kernel_launches += launches;
+    // report the launches that did work, not the no-op tail queued behind the `done` poll
+    stats->extend_launches += std::min<uint64_t>(ext_launches, c.iterations);
+    stats->shade_launches += std::min<uint64_t>(shd_launches, c.iterations);
+    stats->nodes_visited += c.counters[0];
+    stats->tris_tested += c.counters[1];
+    stats->instances_entered += c.counters[2];
+    stats->prims_tested += c.counters[3];
+    stats->mesh_hits += c.counters[4];
+    stats->texel_taps += c.counters[5];
+    stats->material_fetches += c.counters[6];
+    float ms = 0.0f;
+    cudaEventElapsedTime(&ms, ev_begin, ev_end);
+    stats->ms_total += ms;
+    // only iterations that actually had rays count as launches of the dominant kernel
+    double me = 0.0, msd = 0.0;
+    size_t live = std::min<size_t>(timed_iters, c.iterations);
+    for (size_t i = 0; i < live; ++i) {
+      float a = 0.0f, b = 0.0f;
+      cudaEventElapsedTime(&a, s->events[ev_iter_base + 3 * i], s->events[ev_iter_base + 3 * i + 1]);
+      cudaEventElapsedTime(&b, s->events[ev_iter_base + 3 * i + 1], s->events[ev_iter_base + 3 * i + 2]);
+      me += a;
+      msd += b;
+    }
+    if (live && live < c.iterations) {  // more iterations than event slots: scale up
+      double f = (double)c.iterations / (double)live;
+      me *= f;
+      msd *= f;
+    }
+    stats->ms_extend += me;
+    stats->ms_shade += msd;
+  }
+  return RT_OK;
+}
+
+}  // namespace
+
+// ====================================================================== C ABI
+extern "C" {
+
+int rt_abi_version(void) { return RT_B200_ABI_VERSION; }
+const char* rt_last_error(void) { return g_err.c_str(); }
+int rt_device_count(void) {
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess) return fail(RT_ERR_CUDA, std::string("cudaGetDeviceCount: ") + cudaGetErrorString(e));
+  return n;
+}
+
+int rt_scene_create(rt_scene** out) {
+  if (!out) return fail(RT_ERR_INVALID, "out is NULL");
+  *out = new (std::nothrow) rt_scene();
+  return *out ? RT_OK : fail(RT_ERR_INVALID, "out of memory");
+}
+
+void rt_scene_destroy(rt_scene* s) {
+  if (!s) return;
+  if (s->device >= 0 && cudaSetDevice(s->device) == cudaSuccess) {
+    free_wavefront(s);
+    free_buf(s->d_nodes); free_buf(s->d_tris); free_buf(s->d_shade); free_buf(s->d_objects);
+    free_buf(s->d_mats); free_buf(s->d_textures); free_buf(s->d_texels); free_buf(s->d_planes);
+    free_buf(s->d_accum); free_buf(s->d_linear); free_buf(s->d_rgb8); free_buf(s->d_dbg);
+    if (s->ctrl) cudaFree(s->ctrl);
+    if (s->h_ctrl) cudaFreeHost(s->h_ctrl);
+    if (s->h_done) cudaFreeHost(s->h_done);
+    for (auto e : s->events) cudaEventDestroy(e);
+    for (auto e : s->poll_ev) if (e) cudaEventDestroy(e);
+    if (s->own_stream) cudaStreamDestroy(s->own_stream);
+  }
+  delete s;
+}
+
+int rt_add_texture(rt_scene* s, const uint8_t* rgb8, uint32_t w, uint32_t h) {
+  if (!s || !rgb8 || !w || !h) return fail(RT_ERR_INVALID, "rt_add_texture: bad argument");
+  rt::HostTexture t;
+  t.w = w;
+  t.h = h;
+  t.rgba.resize((size_t)w * h);
+  for (size_t i = 0; i < (size_t)w * h; ++i)
+    t.rgba[i] = (uint32_t)rgb8[3 * i] | ((uint32_t)rgb8[3 * i + 1] << 8) | ((uint32_t)rgb8[3 * i + 2] << 16) | 0xFF000000u;
+  s->textures.push_back(std::move(t));
+  s->lowered = false;
+  return (int)s->textures.size() - 1;
+}
+
+int rt_add_material(rt_scene* s, const rt_material_desc* d) {
+  if (!s || !d) return fail(RT_ERR_INVALID, "rt_add_material: bad argument");
+  if (d->tag > RT_MAT_ISOTROPIC) return fail(RT_ERR_INVALID, "rt_add_material: unknown material tag");
+  s->materials.push_back(*d);
+  s->lowered = false;
+  return (int)s->materials.size() - 1;
+}
+
+int rt_add_mesh(rt_scene* s, const float* pos, const float* nrm, const float* uv, uint32_t nverts, const uint32_t* idx,
+                uint32_t ntris) {
+  if (!s || !pos || !nrm || !uv || !idx || !nverts || !ntris) return fail(RT_ERR_INVALID, "rt_add_mesh: bad argument");
+  for (size_t i = 0; i < 3 * (size_t)ntris; ++i)
+    if (idx[i] >= nverts) return fail(RT_ERR_INVALID, "rt_add_mesh: index out of range");
+  rt::HostMesh m;
+  m.pos.assign(pos, pos + 3 * (size_t)nverts);
+  m.nrm.assign(nrm, nrm + 3 * (size_t)nverts);
+  m.uv.assign(uv, uv + 2 * (size_t)nverts);
+  m.idx.assign(idx, idx + 3 * (size_t)ntris);
+  rt::build_mesh(m);
+  s->meshes.push_back(std::move(m));
+  s->lowered = false;
+  return (int)s->meshes.size() - 1;
+}
+
+int rt_add_instance(rt_scene* s, int mesh, const float xform[16], const float* inv_xform, int material, const int tex[5]) {
+  if (!s || !xform) return fail(RT_ERR_INVALID, "rt_add_instance: bad argument");
+  if (mesh < 0 || mesh >= (int)s->meshes.size()) return fail(RT_ERR_INVALID, "rt_add_instance: bad mesh id");
+  if (material >= (int)s->materials.size()) return fail(RT_ERR_INVALID, "rt_add_instance: bad material id");
+  rt::HostObject o;
+  o.kind = RT_OBJ_MESH;
+  o.mesh = mesh;
+  std::memcpy(o.xform, xform, 64);
+  if (inv_xform) {
+    std::memcpy(o.inv_xform, inv_xform, 64);
+  } else if (!rt::invert_affine_cofactor(xform, o.inv_xform)) {
+    return fail(RT_ERR_INVALID, "rt_add_instance: transform is singular (the reference panics here, geometry.rs:168)");
+  }
+  o.material = material < 0 ? -1 : material;
+  for (int k = 0; k < 5; ++k) {
+    o.tex[k] = tex ? tex[k] : -1;
+    if (o.tex[k] >= (int)s->textures.size()) return fail(RT_ERR_INVALID, "rt_add_instance: bad texture id");
+    if (o.tex[k] < 0) o.tex[k] = -1;
+  }
+  s->objects.push_back(o);
+  s->lowered = false;
+  return (int)s->objects.size() - 1;
+}
+
+static int add_simple(rt_scene* s, rt::HostObject& o, int material, const char* who) {
+  if (material < 0 || material >= (int)s->materials.size()) return fail(RT_ERR_INVALID, std::string(who) + ": bad material id");
+  o.material = material;
+  s->objects.push_back(o);
+  s->lowered = false;
+  return (int)s->objects.size() - 1;
+}
+int rt_add_sphere(rt_scene* s, const float c[3], float radius, int material) {
+  if (!s || !c) return fail(RT_ERR_INVALID, "rt_add_sphere: bad argument");
+  rt::HostObject o;
+  o.kind = RT_OBJ_SPHERE;
+  std::memcpy(o.a, c, 12);
+  o.radius = radius;
+  return add_simple(s, o, material, "rt_add_sphere");
+}
+int rt_add_triangle(rt_scene* s, const float a[3], const float b[3], const float c[3], int material) {
+  if (!s || !a || !b || !c) return fail(RT_ERR_INVALID, "rt_add_triangle: bad argument");
+  rt::HostObject o;
+  o.kind = RT_OBJ_TRIANGLE;
+  std::memcpy(o.a, a, 12);
+  std::memcpy(o.b, b, 12);
+  std::memcpy(o.c, c, 12);
+  return add_simple(s, o, material, "rt_add_triangle");
+}
+int rt_add_plane(rt_scene* s, const float p[3], const float n[3], int material) {
+  if (!s || !p || !n) return fail(RT_ERR_INVALID, "rt_add_plane: bad argument");
+  rt::HostObject o;
+  o.kind = RT_OBJ_PLANE;
+  std::memcpy(o.a, p, 12);
+  std::memcpy(o.b, n, 12);
+  return add_simple(s, o, material, "rt_add_plane");
+}
+int rt_add_volume_sphere(rt_scene* s, const float c[3], float radius, float density, int phase_material) {
+  if (!s || !c) return fail(RT_ERR_INVALID, "rt_add_volume_sphere: bad argument");
+  rt::HostObject o;
+  o.kind = RT_OBJ_VOLUME;
+  std::memcpy(o.a, c, 12);
+  o.radius = radius;
+  o.density = density;
+  o.vol_index = s->n_volumes;
+  int rc = add_simple(s, o, phase_material, "rt_add_volume_sphere");
+  if (rc >= 0) s->n_volumes++;
+  return rc;
+}
+
+int rt_scene_upload(rt_scene* s) {
+  if (!s || !s->lowered) return fail(RT_ERR_NOT_COMMITTED, "rt_scene_upload: scene has not been lowered (call rt_commit)");
+  CUDA_TRY(cudaSetDevice(s->device));
+  const rt::Lowered& L = s->low;
+  int rc;
+  cudaStream_t st = 0;
+  if ((rc = upload(s->d_nodes, L.nodes.data(), L.nodes.size() * 16, st)) != RT_OK) return rc;
+  if ((rc = upload(s->d_tris, L.tris.data(), L.tris.size() * 16, st)) != RT_OK) return rc;
+  if ((rc = upload(s->d_shade, L.shade.data(), L.shade.size() * 16, st)) != RT_OK) return rc;
+  if ((rc = upload(s->d_objects, L.objects.data(), L.objects.size() * 16, st)) != RT_OK) return rc;
+  if ((rc = upload(s->d_mats, L.mats.data(), L.mats.size() * 16, st)) != RT_OK) return rc;
+  if ((rc = upload(s->d_textures, L.textures.data(), L.textures.size() * 16, st)) != RT_OK) return rc;
+  if ((rc = upload(s->d_texels, L.texels.data(), L.texels.size() * 4, st)) != RT_OK) return rc;
+  if ((rc = upload(s->d_planes, L.planes.data(), L.planes.size() * 4, st)) != RT_OK) return rc;
+  CUDA_TRY(cudaStreamSynchronize(st));
+  rt_dev_scene& d = s->dev;
+  d.nodes = s->d_nodes.p; d.tris = s->d_tris.p; d.shade = s->d_shade.p; d.objects = s->d_objects.p;
+  d.mats = s->d_mats.p; d.textures = s->d_textures.p; d.texels = s->d_texels.p; d.planes = s->d_planes.p;
+  d.tlas_root = L.tlas_root;
+  d.n_planes = (L.planes.size() == 1 && L.planes[0] < 0) ? 0u : (uint32_t)L.planes.size();
+  d.n_objects = (uint32_t)s->objects.size();
+  d.n_volumes = L.n_volumes;
+  for (int k = 0; k < 3; ++k) {
+    d.tlas_min[k] = L.tlas_min[k];
+    d.tlas_max[k] = L.tlas_max[k];
+  }
+  s->committed = true;
+  return RT_OK;
+}
+
+int rt_commit(rt_scene* s, int device) {
+  if (!s) return fail(RT_ERR_INVALID, "scene is NULL");
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0)
+    return fail(RT_ERR_CUDA, std::string("no usable CUDA device (there is no CPU fallback): ") +
+                                 (e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0"));
+  if (device < 0 || device >= n) return fail(RT_ERR_INVALID, "rt_commit: bad device index");
+  if (s->device >= 0 && s->device != device) return fail(RT_ERR_INVALID, "rt_commit: scene is already bound to another device");
+  std::string err;
+  int rc = rt::lower_scene(s->textures, s->materials, s->meshes, s->objects, s->low, err);
+  if (rc != RT_OK) return fail(rc, err);
+  s->lowered = true;
+  s->device = device;
+  return rt_scene_upload(s);
+}
+
+uint64_t rt_scene_device_bytes(const rt_scene* s) { return s && s->lowered ? s->low.bytes() : 0; }
+
+size_t rt_accum_bytes(uint32_t width, uint32_t height) { return (size_t)width * height * 4 * sizeof(long long); }
+
+int rt_render_accum(rt_scene* s, const rt_camera* cam, const rt_render_opts* opts, void* d_accum, void* stream,
+                    rt_stats* stats) {
+  int rc = set_device(s);
+  if (rc != RT_OK) return rc;
+  if ((rc = check_camera(cam)) != RT_OK) return rc;
+  if (!d_accum) return fail(RT_ERR_INVALID, "d_accum is NULL");
+  rt_render_opts o{};
+  if (opts) o = *opts;
+  rt_frame fr;
+  fill_frame_camera(*cam, o.seed, fr);
+  unsigned long long total = 0;
+  if ((rc = plan_shard(*cam, o, fr, total)) != RT_OK) return rc;
+  fr.capacity = pick_capacity(total, o.wavefront);
+  if (stats) std::memset(stats, 0, sizeof *stats);
+  if (total == 0) return RT_OK;
+  cudaStream_t st = stream ? (cudaStream_t)stream : s->own_stream;
+  if (!stream) {
+    // first use: own_stream is created by ensure_wavefront
+    if ((rc = ensure_wavefront(s, fr.capacity)) != RT_OK) return rc;
+    st = s->own_stream;
+  }
+  rt::rt_debug dbg{nullptr, nullptr, nullptr};
+  return run_wavefront(s, fr, total, (long long*)d_accum, (o.flags & RT_OPT_COUNTERS) != 0, false, dbg, false,
+                       (o.flags & RT_OPT_NO_EVENTS) == 0, st, stats);
+}
+
+int rt_resolve(rt_scene* s, const rt_camera* cam, const void* d_accum, uint32_t total_spp, float* d_out_linear,
+               uint8_t* d_out_rgb8, void* stream) {
+  int rc = set_device(s);
+  if (rc != RT_OK) return rc;
+  if (!cam || !d_accum || !total_spp) return fail(RT_ERR_INVALID, "rt_resolve: bad argument");
+  cudaStream_t st = stream ? (cudaStream_t)stream : 0;
+  rt::launch_resolve((const long long*)d_accum, cam->screen_width * cam->screen_height, total_spp, cam->gamma,
+                     d_out_linear, d_out_rgb8, st);
+  CUDA_TRY(cudaGetLastError());
+  return RT_OK;
+}
+
+int rt_render(rt_scene* s, const rt_camera* cam, const rt_render_opts* opts, float* out_linear, uint8_t* out_rgb8,
+              rt_stats* stats) {
+  int rc = set_device(s);
+  if (rc != RT_OK) return rc;
+  if ((rc = check_camera(cam)) != RT_OK) return rc;
+  size_t npix = (size_t)cam->screen_width * cam->screen_height;
+  if ((rc = ensure_buf(s->d_accum, rt_accum_bytes(cam->screen_width, cam->screen_height))) != RT_OK) return rc;
+  if ((rc = ensure_wavefront(s, 128)) != RT_OK) return rc;
+  cudaStream_t st = s->own_stream;
+  CUDA_TRY(cudaMemsetAsync(s->d_accum.p, 0, rt_accum_bytes(cam->screen_width, cam->screen_height), st));
+  rt_stats local{};
+  if ((rc = rt_render_accum(s, cam, opts, s->d_accum.p, st, &local)) != RT_OK) return rc;
+  // how many samples per pixel ended up in the accumulator
+  rt_render_opts o{};
+  if (opts) o = *opts;
+  rt_frame fr;
+  fill_frame_camera(*cam, o.seed, fr);
+  unsigned long long total = 0;
+  if ((rc = plan_shard(*cam, o, fr, total)) != RT_OK) return rc;
+  uint32_t spp = total ? fr.sample_count : 1;
+  cudaEvent_t e0, e1;
+  CUDA_TRY(cudaEventCreate(&e0));
+  CUDA_TRY(cudaEventCreate(&e1));
+  if (out_linear && (rc = ensure_buf(s->d_linear, npix * 12)) != RT_OK) return rc;
+  if (out_rgb8 && (rc = ensure_buf(s->d_rgb8, npix * 3)) != RT_OK) return rc;
+  CUDA_TRY(cudaEventRecord(e0, st));
+  rt::launch_resolve((const long long*)s->d_accum.p, (uint32_t)npix, spp, cam->gamma,
+                     out_linear ? (float*)s->d_linear.p : nullptr, out_rgb8 ? (uint8_t*)s->d_rgb8.p : nullptr, st);
+  CUDA_TRY(cudaEventRecord(e1, st));
+  local.kernel_launches += 1;
+  if (out_linear) {
+    CUDA_TRY(cudaMemcpyAsync(out_linear, s->d_linear.p, npix * 12, cudaMemcpyDeviceToHost, st));
+    local.d2h_bytes += npix * 12;
+  }
+  if (out_rgb8) {
+    CUDA_TRY(cudaMemcpyAsync(out_rgb8, s->d_rgb8.p, npix * 3, cudaMemcpyDeviceToHost, st));
+    local.d2h_bytes += npix * 3;
+  }
+  CUDA_TRY(cudaStreamSynchronize(st));
+  float ms = 0.0f;
+  cudaEventElapsedTime(&ms, e0, e1);
+  local.ms_resolve = ms;
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  local.h2d_bytes += sizeof(rt_frame) + sizeof(rt_dev_scene);  // kernel parameters
+  local.d2h_bytes += sizeof(rt_ctrl);
+  if (stats) *stats = local;
+  return RT_OK;
+}
+
+// ---- parity hooks: one k_extend launch in debug mode, results copied back
+static int trace_common(rt_scene* s, const rt_frame& fr, unsigned long long total, uint32_t n, const float* ray_od,
+                        int32_t* obj_id, int32_t* prim_id, float* t, float* normal_xyz, float* hitpoint_xyz, float* uv,
+                        int32_t* frontface, float* ray_out) {
+  int rc = ensure_wavefront(s, fr.capacity);
+  if (rc != RT_OK) return rc;
+  cudaStream_t st = s->own_stream;
+  if ((rc = ensure_buf(s->d_dbg, (size_t)n * 12)) != RT_OK) return rc;
+  rt::rt_debug dbg;
+  dbg.obj = (int32_t*)s->d_dbg.p;
+  dbg.prim = dbg.obj + n;
+  dbg.t = (float*)(dbg.prim + n);
+  std::vector<float> A, B, C;
+  if (ray_od) {
+    // caller-supplied rays become "continuing" rays: pixel = i, sample 0, bounce 0
+    A.resize((size_t)n * 4); B.resize((size_t)n * 4); C.resize((size_t)n * 4);
+    for (uint32_t i = 0; i < n; ++i) {
+      const float* p = ray_od + (size_t)i * 6;
+      A[4 * i] = p[0]; A[4 * i + 1] = p[1]; A[4 * i + 2] = p[2]; A[4 * i + 3] = p[3];
+      B[4 * i] = p[4]; B[4 * i + 1] = p[5]; B[4 * i + 2] = 1.0f; B[4 * i + 3] = 1.0f;
+      C[4 * i] = 1.0f;
+      uint32_t px = i, sb = 0;
+      std::memcpy(&C[4 * i + 1], &px, 4);
+      std::memcpy(&C[4 * i + 2], &sb, 4);
+      C[4 * i + 3] = 0.0f;
+    }
+    CUDA_TRY(cudaMemcpyAsync(s->paths[0].A, A.data(), (size_t)n * 16, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(s->paths[0].B, B.data(), (size_t)n * 16, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(s->paths[0].C, C.data(), (size_t)n * 16, cudaMemcpyHostToDevice, st));
+  }
+  rt_frame f2 = fr;
+  // single iteration; with supplied rays the control block starts with n_next = n and no new work
+  rt::launch_init(s->ctrl, ray_od ? 0ull : total, st);
+  if (ray_od) CUDA_TRY(cudaMemcpyAsync(&s->ctrl->n_next, &n, 4, cudaMemcpyHostToDevice, st));
+  rt::launch_advance(s->ctrl, f2.capacity, st);
+  rt::launch_extend(s->dev, f2, s->ctrl, s->paths[0], s->hits, s->queues, dbg, false, true, st);
+  CUDA_TRY(cudaGetLastError());
+  std::vector<float> H0((size_t)n * 4), H1((size_t)n * 4);
+  std::vector<uint32_t> H2(n);
+  std::vector<int32_t> o(n), p(n);
+  std::vector<float> tt(n);
+  CUDA_TRY(cudaMemcpyAsync(H0.data(), s->hits.H0, (size_t)n * 16, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaMemcpyAsync(H1.data(), s->hits.H1, (size_t)n * 16, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaMemcpyAsync(H2.data(), s->hits.H2, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaMemcpyAsync(o.data(), dbg.obj, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaMemcpyAsync(p.data(), dbg.prim, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaMemcpyAsync(tt.data(), dbg.t, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
+  if (ray_out) {
+    A.resize((size_t)n * 4); B.resize((size_t)n * 4);
+    CUDA_TRY(cudaMemcpyAsync(A.data(), s->paths[0].A, (size_t)n * 16, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(B.data(), s->paths[0].B, (size_t)n * 16, cudaMemcpyDeviceToHost, st));
+  }
+  CUDA_TRY(cudaStreamSynchronize(st));
+  for (uint32_t i = 0; i < n; ++i) {
+    bool hit = o[i] >= 0;
+    if (obj_id) obj_id[i] = o[i];
+    if (prim_id) prim_id[i] = p[i];
+    if (t) t[i] = tt[i];
+    if (normal_xyz) {
+      normal_xyz[3 * i] = hit ? H0[4 * i + 3] : 0.0f;
+      normal_xyz[3 * i + 1] = hit ? H1[4 * i] : 0.0f;
+      normal_xyz[3 * i + 2] = hit ? H1[4 * i + 1] : 0.0f;
+    }
+    if (hitpoint_xyz)
+      for (int k = 0; k < 3; ++k) hitpoint_xyz[3 * i + k] = hit ? H0[4 * i + k] : 0.0f;
+    if (uv) {
+      uv[2 * i] = hit ? H1[4 * i + 2] : 0.0f;
+      uv[2 * i + 1] = hit ? H1[4 * i + 3] : 0.0f;
+    }
+    if (frontface) frontface[i] = hit ? (int32_t)((H2[i] >> 3) & 1u) : 0;
+    if (ray_out) {
+      float* r = ray_out + (size_t)i * 6;
+      r[0] = A[4 * i]; r[1] = A[4 * i + 1]; r[2] = A[4 * i + 2]; r[3] = A[4 * i + 3];
+      r[4] = B[4 * i]; r[5] = B[4 * i + 1];
+    }
+  }
+  return RT_OK;
+}
+
+int rt_trace_primary(rt_scene* s, const rt_camera* cam, uint64_t seed, uint32_t sample, int32_t* obj_id,
+                     int32_t* prim_id, float* t, float* normal_xyz, float* ray_od) {
+  int rc = set_device(s);
+  if (rc != RT_OK) return rc;
+  if ((rc = check_camera(cam)) != RT_OK) return rc;
+  if (sample >= cam->aa_sample_count) return fail(RT_ERR_INVALID, "rt_trace_primary: sample >= aa_sample_count");
+  rt_frame fr;
+  fill_frame_camera(*cam, seed, fr);
+  fr.sample_begin = sample;
+  fr.sample_count = 1;
+  unsigned long long total = (unsigned long long)cam->screen_width * cam->screen_height;
+  if (total > (1ull << 27)) return fail(RT_ERR_INVALID, "rt_trace_primary: image too large for one wavefront");
+  fr.capacity = (uint32_t)((total + 127) / 128 * 128);
+  return trace_common(s, fr, total, (uint32_t)total, nullptr, obj_id, prim_id, t, normal_xyz, nullptr, nullptr, nullptr,
+                      ray_od);
+}
+
+int rt_intersect_rays(rt_scene* s, uint64_t seed, uint32_t n, const float* ray_od, float t_min, float t_max,
+                      int32_t* obj_id, int32_t* prim_id, float* t, float* normal_xyz, float* hitpoint_xyz, float* uv,
+                      int32_t* frontface) {
+  int rc = set_device(s);
+  if (rc != RT_OK) return rc;
+  if (!ray_od) return fail(RT_ERR_INVALID, "rt_intersect_rays: ray_od is NULL");
+  if (n == 0) return RT_OK;
+  if (n > (1u << 27)) return fail(RT_ERR_INVALID, "rt_intersect_rays: too many rays for one wavefront");
+  rt_frame fr;
+  std::memset(&fr, 0, sizeof fr);
+  fr.k0 = (uint32_t)seed;
+  fr.k1 = (uint32_t)(seed >> 32);
+  fr.t_min = t_min;
+  fr.t_max = t_max;
+  fr.width = n; fr.height = 1; fr.spp = 1; fr.rooti = 1; fr.sample_count = 1; fr.path_depth = 1;
+  fr.shard_count = 1;
+  fr.capacity = (n + 127) / 128 * 128;
+  return trace_common(s, fr, 0, n, ray_od, obj_id, prim_id, t, normal_xyz, hitpoint_xyz, uv, frontface, nullptr);
+}
+
+// ---- assets
+int rt_obj_parse(const char* text, size_t len, rt_obj_mesh* out) {
+  if (!text || !out) return fail(RT_ERR_INVALID, "rt_obj_parse: bad argument");
+  std::string err;
+  int rc = rt::obj_parse(text, len, out, err);
+  return rc == RT_OK ? RT_OK : fail(rc, err);
+}
+int rt_obj_load(const char* path, rt_obj_mesh* out) {
+  if (!path || !out) return fail(RT_ERR_INVALID, "rt_obj_load: bad argument");
+  FILE* f = std::fopen(path, "rb");
+  if (!f) return fail(RT_ERR_IO, std::string("cannot open ") + path);
+  std::string data;
+  char buf[1 << 16];
+  size_t n;
+  while ((n = std::fread(buf, 1, sizeof buf, f)) > 0) data.append(buf, n);
+  std::fclose(f);
+  return rt_obj_parse(data.data(), data.size(), out);
+}
+void rt_obj_free(rt_obj_mesh* m) {
+  if (!m) return;
+  std::free(m->pos); std::free(m->nrm); std::free(m->uv); std::free(m->idx);
+  std::memset(m, 0, sizeof *m);
+}
+int rt_tga_decode(const uint8_t* bytes, size_t len, uint8_t** rgb, uint32_t* w, uint32_t* h) {
+  if (!bytes || !rgb || !w || !h) return fail(RT_ERR_INVALID, "rt_tga_decode: bad argument");
+  std::string err;
+  int rc = rt::tga_decode(bytes, len, rgb, w, h, err);
+  return rc == RT_OK ? RT_OK : fail(rc, err);
+}
+int rt_tga_encode_rgb8(const uint8_t* rgb, uint32_t w, uint32_t h, uint8_t** bytes, size_t* len) {
+  int rc = rt::tga_encode_rgb8(rgb, w, h, bytes, len);
+  return rc == RT_OK ? RT_OK : fail(rc, "rt_tga_encode_rgb8: bad argument");
+}
+void rt_free(void* p) { std::free(p); }
+
+int rt_mesh_reachability(const float* pos, uint32_t nverts, const uint32_t* idx, uint32_t ntris, uint8_t* mask) {
+  if (!pos || !idx || !mask) return fail(RT_ERR_INVALID, "rt_mesh_reachability: bad argument");
+  for (size_t i = 0; i < 3 * (size_t)ntris; ++i)
+    if (idx[i] >= nverts) return fail(RT_ERR_INVALID, "rt_mesh_reachability: index out of range");
+  rt::mesh_reachability(pos, idx, ntris, mask);
+  return RT_OK;
+}
+
+}  // extern "C"

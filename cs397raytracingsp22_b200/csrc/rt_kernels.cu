@@ -1,0 +1,908 @@
+// rt_kernels.cu — hand-written sm_100a kernels of the wavefront path tracer.
+//
+//   k_advance : 1 thread; wavefront bookkeeping between bounces (device-side, no host sync)
+//   k_extend  : ray-gen (Camera::generate_rays, tracing.rs:159-209) fused with the closest-hit
+//               query (Scene::intersect_ray tracing.rs:327-346 and everything under it:
+//               geometry.rs:50-123,300-366,394-526), hit resolution (geometry.rs:253-298,350-363)
+//               and material-sorted enqueue (match/ballot compaction)
+//   k_shade   : Material::scatter / emission (materials.rs:33-166) + the integrator step of
+//               Scene::shade_ray (tracing.rs:300-324), one warp-uniform material class per warp
+//   k_resolve : mean + output transform (tracing.rs:241-256)
+//
+// Arithmetic contract: this file is compiled with -fmad=false.  Everything that decides WHICH
+// primitive is hit (object-space transform, Möller–Trumbore, sphere, plane, volume entry/exit)
+// is a sequence of single IEEE f32 operations in the reference's order, so primary-hit ids are
+// bit-exact against the strict-IEEE CPU oracle.  BVH slab tests only cull, are conservative
+// (padded boxes, non-strict compare) and use explicit FMAs and approximate reciprocals.
+//
+// No tensor cores: there is no dense contraction anywhere in this workload.
+
+#include <cuda_runtime.h>
+#include <math_constants.h>
+#include <stdint.h>
+
+#include "rt_kernels.h"
+
+namespace rt {
+
+#define RT_BLOCK 128
+#define RT_WARPS (RT_BLOCK / 32)
+#define RT_SMEM_STACK 16   // traversal-stack entries per thread kept in shared memory
+#define RT_LOCAL_STACK 48  // overflow entries (local memory; host checks depth <= 62)
+
+// ------------------------------------------------------------------ small vector helpers
+struct f3 {
+  float x, y, z;
+};
+__device__ __forceinline__ f3 mk(float x, float y, float z) { return f3{x, y, z}; }
+__device__ __forceinline__ f3 operator+(f3 a, f3 b) { return mk(a.x + b.x, a.y + b.y, a.z + b.z); }
+__device__ __forceinline__ f3 operator-(f3 a, f3 b) { return mk(a.x - b.x, a.y - b.y, a.z - b.z); }
+__device__ __forceinline__ f3 operator-(f3 a) { return mk(-a.x, -a.y, -a.z); }
+__device__ __forceinline__ f3 operator*(f3 a, float s) { return mk(a.x * s, a.y * s, a.z * s); }
+__device__ __forceinline__ f3 operator*(float s, f3 a) { return mk(a.x * s, a.y * s, a.z * s); }
+__device__ __forceinline__ f3 operator/(f3 a, float s) { return mk(a.x / s, a.y / s, a.z / s); }
+__device__ __forceinline__ f3 mulv(f3 a, f3 b) { return mk(a.x * b.x, a.y * b.y, a.z * b.z); }
+__device__ __forceinline__ float dot(f3 a, f3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }  // (x+y)+z
+__device__ __forceinline__ float mag2(f3 a) { return dot(a, a); }
+__device__ __forceinline__ f3 cross(f3 a, f3 b) {
+  return mk(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x);
+}
+__device__ __forceinline__ f3 normalize(f3 a) { return a * (1.0f / sqrtf(mag2(a))); }  // v * (1/|v|)
+__device__ __forceinline__ float clampf(float v, float lo, float hi) { return v < lo ? lo : (v > hi ? hi : v); }
+
+__device__ __forceinline__ float4 ldq(const void* base, uint32_t quad) {
+  return __ldg(reinterpret_cast<const float4*>(base) + quad);
+}
+__device__ __forceinline__ uint32_t fbits(float f) { return __float_as_uint(f); }
+
+// ------------------------------------------------------------------ RNG contract
+struct u4 {
+  uint32_t x, y, z, w;
+};
+__device__ __forceinline__ u4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0,
+                                            uint32_t k1) {
+  const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    uint32_t hi0 = __umulhi(M0, c0), lo0 = M0 * c0;
+    uint32_t hi1 = __umulhi(M1, c2), lo1 = M1 * c2;
+    uint32_t n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
+    c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+    k0 += W0; k1 += W1;
+  }
+  return u4{c0, c1, c2, c3};
+}
+__device__ __forceinline__ float u01(uint32_t x) { return (float)(x >> 8) * (1.0f / 16777216.0f); }
+#define RT_BOUNCE_CAMERA 0xFFFFFFFFu
+#define RT_PI 3.14159265358979323846f
+
+// uniform point of the unit ball (stands in for rand_sphere_vec, tracing.rs:71-79; NOT normalised)
+__device__ __forceinline__ f3 ball_from(uint32_t a, uint32_t b, uint32_t c) {
+  float rad = cbrtf(u01(a));
+  float zc = 1.0f - 2.0f * u01(b);
+  float s = sqrtf(fmaxf(0.0f, 1.0f - zc * zc));
+  float phi = (2.0f * RT_PI) * u01(c);
+  float sn, cs;
+  sincosf(phi, &sn, &cs);
+  return mk(rad * s * cs, rad * zc, rad * s * sn);
+}
+// uniform point of the unit disk (rand_disk_vec, tracing.rs:81-89)
+__device__ __forceinline__ f3 disk_from(uint32_t a, uint32_t b) {
+  float rr = sqrtf(u01(a));
+  float phi = (2.0f * RT_PI) * u01(b);
+  float sn, cs;
+  sincosf(phi, &sn, &cs);
+  return mk(rr * cs, rr * sn, 0.0f);
+}
+
+// ------------------------------------------------------------------ camera (Q8)
+__device__ __forceinline__ void camera_ray(const rt_frame& fr, uint32_t x, uint32_t y, uint32_t pixel, uint32_t i,
+                                           f3& origin, f3& direction) {
+  u4 r = philox4x32_10(pixel, i, RT_BOUNCE_CAMERA, 0u, fr.k0, fr.k1);
+  float rand_x = (float)__umulhi(r.x, fr.spp);
+  float rand_y = (float)__umulhi(r.y, fr.spp);
+  float subpixel_x = (float)(i / fr.rooti);
+  float subpixel_y = (float)(i % fr.rooti);
+  float ps = fr.pixel_size, n = fr.n, rootn = fr.rootn;
+  float off_x = (subpixel_x - 0.5f * rootn) * ps / rootn + (rand_x - 0.5f * n) * ps / n;
+  float off_y = (subpixel_y - 0.5f * rootn) * ps / rootn + (rand_y - 0.5f * n) * ps / n;
+  f3 center = mk(ps * ((float)x - 0.5f * (float)fr.width + 0.5f) + off_x,
+                 ps * (0.5f + 0.5f * (float)fr.height - (float)y) + off_y, -fr.focal_length);
+  f3 focus = normalize(center) * fr.focus_dist;
+  f3 lens = fr.lens_radius * disk_from(r.z, r.w);
+  f3 dcam = normalize(focus - lens);
+  f3 c0 = mk(fr.rot0[0], fr.rot0[1], fr.rot0[2]), c1 = mk(fr.rot1[0], fr.rot1[1], fr.rot1[2]),
+     c2 = mk(fr.rot2[0], fr.rot2[1], fr.rot2[2]);
+  f3 rl = c0 * lens.x + c1 * lens.y + c2 * lens.z;
+  origin = mk(fr.eye[0], fr.eye[1], fr.eye[2]) + rl;
+  direction = c0 * dcam.x + c1 * dcam.y + c2 * dcam.z;
+}
+
+// work index -> (pixel, sample); false when a tile slot falls outside the image
+__device__ __forceinline__ bool work_to_pixel(const rt_frame& fr, unsigned long long g, uint32_t& x, uint32_t& y,
+                                              uint32_t& sample) {
+  unsigned long long pl = g / fr.sample_count;
+  sample = fr.sample_begin + (uint32_t)(g - pl * fr.sample_count);
+  if (fr.shard_mode == RT_SHARD_TILES) {
+    uint32_t ts = fr.tile_size, ts2 = ts * ts;
+    uint32_t k = (uint32_t)(pl / ts2), within = (uint32_t)(pl - (unsigned long long)k * ts2);
+    uint32_t tile = k * fr.shard_count + fr.shard_rank;
+    uint32_t tx = tile % fr.tiles_x, ty = tile / fr.tiles_x;
+    x = tx * ts + within % ts;
+    y = ty * ts + within / ts;
+    return x < fr.width && y < fr.height;
+  }
+  uint32_t p = (uint32_t)pl;
+  y = p / fr.width;
+  x = p - y * fr.width;
+  return true;
+}
+
+// ------------------------------------------------------------------ closest hit
+struct Best {
+  float t;
+  float u, v;    // mesh barycentrics
+  int obj;       // top-level object index, -1 = miss
+  uint32_t prim; // original triangle index inside the mesh
+};
+struct Cnt {
+  uint32_t nodes, tris, inst, prims;
+};
+
+// reference ordering of candidates: smaller t wins; equal t: earlier object wins (strict '<' in
+// tracing.rs:335); same mesh and equal t: higher triangle index wins (geometry.rs:105-115,349)
+__device__ __forceinline__ bool better(float t, int obj, uint32_t prim, const Best& b) {
+  if (b.obj < 0) return true;
+  if (t < b.t) return true;
+  if (t > b.t) return false;
+  if (obj != b.obj) return obj < b.obj;
+  return prim > b.prim;
+}
+
+// conservative slab test; returns entry distance in tn
+__device__ __forceinline__ bool slab(float4 lo, float4 hi, f3 inv, f3 oi, float tmin, float tmax, float& tn) {
+  float x0 = __fmaf_rn(lo.x, inv.x, oi.x), x1 = __fmaf_rn(hi.x, inv.x, oi.x);
+  float y0 = __fmaf_rn(lo.y, inv.y, oi.y), y1 = __fmaf_rn(hi.y, inv.y, oi.y);
+  float z0 = __fmaf_rn(lo.z, inv.z, oi.z), z1 = __fmaf_rn(hi.z, inv.z, oi.z);
+  float a = fmaxf(fmaxf(fminf(x0, x1), fminf(y0, y1)), fmaxf(fminf(z0, z1), tmin));
+  float b = fminf(fminf(fmaxf(x0, x1), fmaxf(y0, y1)), fminf(fmaxf(z0, z1), tmax));
+  tn = a;
+  return a <= b * 1.0000005f;
+}
+__device__ __forceinline__ uint32_t pack_entry(float4 lo, float4 hi) {
+  uint32_t lf = fbits(lo.w), cnt = fbits(hi.w);
+  return cnt ? (RT_LEAF_FLAG | (lf << 4) | cnt) : lf;
+}
+__device__ __forceinline__ f3 approx_inv(f3 d) {
+  return mk(__fdividef(1.0f, d.x), __fdividef(1.0f, d.y), __fdividef(1.0f, d.z));
+}
+
+// Sphere::intersect_ray core (geometry.rs:397-410): returns t or NaN-free miss flag
+__device__ __forceinline__ bool sphere_t(f3 center, float radius, f3 o, f3 d, float t_min, float t_max, float& t) {
+  f3 f = o - center;
+  float a = mag2(d);
+  float b = 2.0f * dot(f, d);
+  float c = mag2(f) - radius * radius;
+  float disc = b * b - 4.0f * a * c;
+  if (disc < 0.0f) return false;
+  float sq = sqrtf(disc);
+  float t1 = (-b - sq) / (2.0f * a);
+  float t2 = (-b + sq) / (2.0f * a);
+  t = t1 >= t_min ? t1 : t2;
+  return !(t < t_min || t > t_max);
+}
+
+template <bool COUNT>
+__device__ __forceinline__ void closest_hit(const rt_dev_scene& sc, f3 wo, f3 wd, float t_min, float t_max,
+                                            uint32_t k0, uint32_t k1, uint32_t pixel, uint32_t sample,
+                                            uint32_t bounce, uint32_t* sstack, Best& best, Cnt& cnt) {
+  best.t = t_max;
+  best.obj = -1;
+  best.prim = 0;
+  best.u = best.v = 0.0f;
+  uint32_t lstack[RT_LOCAL_STACK];
+  int sp = 0;
+  const uint32_t tid = threadIdx.x;
+#define RT_PUSH(val)                                        \
+  do {                                                      \
+    if (sp < RT_SMEM_STACK) sstack[sp * RT_BLOCK + tid] = (val); \
+    else lstack[sp - RT_SMEM_STACK] = (val);                \
+    ++sp;                                                   \
+  } while (0)
+#define RT_POP(dst)                                         \
+  do {                                                      \
+    --sp;                                                   \
+    (dst) = sp < RT_SMEM_STACK ? sstack[sp * RT_BLOCK + tid] : lstack[sp - RT_SMEM_STACK]; \
+  } while (0)
+
+  f3 o = wo, d = wd;
+  f3 inv = approx_inv(d);
+  f3 oi = mk(-o.x * inv.x, -o.y * inv.y, -o.z * inv.z);
+  bool in_blas = false;
+  int cur_obj = -1;
+  uint32_t entry = sc.tlas_root;
+  if (entry != RT_ENTRY_NONE) {
+    float tn;
+    float4 lo = make_float4(sc.tlas_min[0], sc.tlas_min[1], sc.tlas_min[2], 0.0f);
+    float4 hi = make_float4(sc.tlas_max[0], sc.tlas_max[1], sc.tlas_max[2], 0.0f);
+    if (!slab(lo, hi, inv, oi, t_min, t_max, tn)) entry = RT_ENTRY_NONE;
+  }
+
+  for (;;) {
+    // descend interior nodes: fetch the 64-byte child pair with four 128-bit read-only loads
+    while (entry != RT_ENTRY_NONE && !(entry & RT_LEAF_FLAG)) {
+      float4 l0 = ldq(sc.nodes, entry * 2u), l1 = ldq(sc.nodes, entry * 2u + 1u);
+      float4 r0 = ldq(sc.nodes, entry * 2u + 2u), r1 = ldq(sc.nodes, entry * 2u + 3u);
+      if (COUNT) cnt.nodes += 2;
+      float tl, tr;
+      bool hl = slab(l0, l1, inv, oi, t_min, best.t, tl);
+      bool hr = slab(r0, r1, inv, oi, t_min, best.t, tr);
+      uint32_t el = pack_entry(l0, l1), er = pack_entry(r0, r1);
+      if (hl && hr) {
+        bool lfirst = tl <= tr;
+        RT_PUSH(lfirst ? er : el);
+        entry = lfirst ? el : er;
+      } else {
+        entry = hl ? el : (hr ? er : RT_ENTRY_NONE);
+      }
+    }
+    if (entry != RT_ENTRY_NONE) {
+      uint32_t first = (entry & ~RT_LEAF_FLAG) >> 4, n = entry & 15u;
+      entry = RT_ENTRY_NONE;
+      if (in_blas) {
+        // IndexedTriangle::intersect_ray, geometry.rs:333-349 (object space, un-normalised d)
+        for (uint32_t k = 0; k < n; ++k) {
+          uint32_t q = (first + k) * RT_TRI_QUADS;
+          float4 a0 = ldq(sc.tris, q), a1 = ldq(sc.tris, q + 1), a2 = ldq(sc.tris, q + 2);
+          if (COUNT) cnt.tris += 1;
+          f3 va = mk(a0.x, a0.y, a0.z), e1 = mk(a0.w, a1.x, a1.y), e2 = mk(a1.z, a1.w, a2.x);
+          f3 qv = cross(d, e2);
+          float g = dot(e1, qv);
+          if (fabsf(g) < 0.0001f) continue;
+          float f = 1.0f / g;
+          f3 s = o - va;
+          float u = f * dot(s, qv);
+          if (u < 0.0f) continue;
+          f3 r = cross(s, e1);
+          float v = f * dot(d, r);
+          if (v < 0.0f || u + v > 1.0f) continue;
+          float t = f * dot(e2, r);
+          if (t < t_min || t > t_max) continue;
+          uint32_t id = fbits(a2.y);
+          if (better(t, cur_obj, id, best)) {
+            best.t = t; best.u = u; best.v = v; best.obj = cur_obj; best.prim = id;
+          }
+        }
+      } else {
+        // TLAS leaf: one top-level object
+        int obj = (int)first;
+        uint32_t q = (uint32_t)obj * RT_OBJ_QUADS;
+        float4 h = ldq(sc.objects, q);
+        int kind = (int)fbits(h.x);
+        if (kind == RT_OBJ_MESH) {
+          float4 r0 = ldq(sc.objects, q + 1), r1 = ldq(sc.objects, q + 2), r2 = ldq(sc.objects, q + 3);
+          float4 m7 = ldq(sc.objects, q + 7);
+          if (COUNT) cnt.inst += 1;
+          // StaticMesh::intersect_ray, geometry.rs:304: transform_point / transform_vector
+          f3 no = mk(r0.x * wo.x + r0.y * wo.y + r0.z * wo.z + r0.w * 1.0f,
+                     r1.x * wo.x + r1.y * wo.y + r1.z * wo.z + r1.w * 1.0f,
+                     r2.x * wo.x + r2.y * wo.y + r2.z * wo.z + r2.w * 1.0f);
+          f3 nd = mk(r0.x * wd.x + r0.y * wd.y + r0.z * wd.z + r0.w * 0.0f,
+                     r1.x * wd.x + r1.y * wd.y + r1.z * wd.z + r1.w * 0.0f,
+                     r2.x * wd.x + r2.y * wd.y + r2.z * wd.z + r2.w * 0.0f);
+          uint32_t root = fbits(m7.x);
+          if (root != RT_ENTRY_NONE) {
+            RT_PUSH(RT_ENTRY_RESTORE);
+            o = no; d = nd;
+            inv = approx_inv(d);
+            oi = mk(-o.x * inv.x, -o.y * inv.y, -o.z * inv.z);
+            in_blas = true;
+            cur_obj = obj;
+            entry = root;
+          }
+        } else {
+          if (COUNT) cnt.prims += 1;
+          float4 q1 = ldq(sc.objects, q + 1);
+          if (kind == RT_OBJ_SPHERE) {
+            float t;
+            if (sphere_t(mk(q1.x, q1.y, q1.z), q1.w, wo, wd, t_min, t_max, t) && better(t, obj, 0u, best)) {
+              best.t = t; best.obj = obj; best.prim = 0;
+            }
+          } else if (kind == RT_OBJ_TRIANGLE) {
+            // Triangle::intersect_ray, geometry.rs:433-447
+            float4 q2 = ldq(sc.objects, q + 2), q3 = ldq(sc.objects, q + 3);
+            f3 va = mk(q1.x, q1.y, q1.z), e1 = mk(q1.w, q2.x, q2.y), e2 = mk(q2.z, q2.w, q3.x);
+            f3 qv = cross(wd, e2);
+            float g = dot(e1, qv);
+            if (!(fabsf(g) < 0.0001f)) {
+              float f = 1.0f / g;
+              f3 s = wo - va;
+              float u = f * dot(s, qv);
+              if (!(u < 0.0f)) {
+                f3 r = cross(s, e1);
+                float v = f * dot(wd, r);
+                if (!(v < 0.0f || u + v > 1.0f)) {
+                  float t = f * dot(e2, r);
+                  if (!(t < t_min || t > t_max) && better(t, obj, 0u, best)) {
+                    best.t = t; best.obj = obj; best.prim = 0;
+                  }
+                }
+              }
+            }
+          } else if (kind == RT_OBJ_VOLUME) {
+            // ConvexVolume::intersect_ray with a Sphere boundary, geometry.rs:505-525
+            float4 q2 = ldq(sc.objects, q + 2);
+            f3 c = mk(q1.x, q1.y, q1.z);
+            float t_entr, t_exit;
+            if (sphere_t(c, q1.w, wo, wd, -CUDART_MAX_NORMAL_F, CUDART_MAX_NORMAL_F, t_entr) &&
+                sphere_t(c, q1.w, wo, wd, t_entr + 0.0001f, CUDART_MAX_NORMAL_F, t_exit) &&
+                !(t_exit < t_min || t_entr > t_max)) {
+              float t_start = fmaxf(t_entr, t_min);
+              float t_end = fminf(t_exit, t_max);
+              float dist_in = t_end - t_start;
+              uint32_t vi = fbits(q2.y);
+              u4 rr = philox4x32_10(pixel, sample, bounce, 1u + (vi >> 2), k0, k1);
+              uint32_t w = (vi & 3u) == 0 ? rr.x : ((vi & 3u) == 1 ? rr.y : ((vi & 3u) == 2 ? rr.z : rr.w));
+              float dist_before = (-1.0f / q2.x) * logf(u01(w));
+              if (dist_before < dist_in) {
+                float t = t_start + dist_before;
+                if (better(t, obj, 0u, best)) {
+                  best.t = t; best.obj = obj; best.prim = 0;
+                }
+              }
+            }
+          }
+        }
+      }
+    }
+    if (entry == RT_ENTRY_NONE) {
+      if (sp == 0) break;
+      RT_POP(entry);
+      if (entry == RT_ENTRY_RESTORE) {
+        o = wo; d = wd;
+        inv = approx_inv(d);
+        oi = mk(-o.x * inv.x, -o.y * inv.y, -o.z * inv.z);
+        in_blas = false;
+        entry = RT_ENTRY_NONE;
+        // fall through to pop the next entry on the next trip round the loop
+        if (sp == 0) break;
+        RT_POP(entry);
+        // a RESTORE marker is never directly below another one
+      }
+    }
+  }
+#undef RT_PUSH
+#undef RT_POP
+
+  // unbounded objects (planes) and anything the TLAS could not bound: always tested
+  const int32_t* planes = reinterpret_cast<const int32_t*>(sc.planes);
+  for (uint32_t pi = 0; pi < sc.n_planes; ++pi) {
+    int obj = __ldg(planes + pi);
+    uint32_t q = (uint32_t)obj * RT_OBJ_QUADS;
+    float4 h = ldq(sc.objects, q);
+    int kind = (int)fbits(h.x);
+    float4 q1 = ldq(sc.objects, q + 1), q2 = ldq(sc.objects, q + 2);
+    if (COUNT) cnt.prims += 1;
+    if (kind == RT_OBJ_PLANE) {
+      // Plane::intersect_ray, geometry.rs:476-485
+      f3 nrm = mk(q2.x, q2.y, q2.z);
+      f3 to = wo - mk(q1.x, q1.y, q1.z);
+      float od = dot(to, nrm);
+      float sg = (od != od) ? od : (signbit(od) ? -1.0f : 1.0f);
+      f3 n = sg * nrm;
+      float dd = dot(wd, n);
+      if (!(dd >= 0.0f)) {
+        float t = fabsf(od) / fabsf(dd);
+        if (!(t < t_min || t > t_max) && better(t, obj, 0u, best)) {
+          best.t = t; best.obj = obj; best.prim = 0;
+        }
+      }
+    }
+  }
+}
+
+// nearest RGB8 tap, texture.rs:28-31 (Q7)
+__device__ __forceinline__ f3 tex_sample(const rt_dev_scene& sc, int tex, float u, float v) {
+  uint4 td = __ldg(reinterpret_cast<const uint4*>(sc.textures) + tex);
+  float fx = clampf(u, 0.0f, 0.999f) * (float)td.y;
+  float fy = (1.0f - clampf(v, 0.0f, 0.999f)) * (float)td.z;
+  // Rust `as u32`: saturating, NaN -> 0
+  uint32_t x = (fx != fx) ? 0u : __float2uint_rz(fx);
+  uint32_t y = (fy != fy) ? 0u : __float2uint_rz(fy);
+  x = min(x, td.y - 1u);
+  y = min(y, td.z - 1u);
+  uint32_t p = __ldg(reinterpret_cast<const uint32_t*>(sc.texels) + td.x + y * td.y + x);
+  return mk((float)(p & 255u) / 255.0f, (float)((p >> 8) & 255u) / 255.0f, (float)((p >> 16) & 255u) / 255.0f);
+}
+
+struct Surface {
+  f3 hp, n;
+  float u, v;
+  uint32_t meta;  // class | frontface << 3 | id << 4   (id: material index, or object index for PARAM_TEX)
+};
+
+// what the reference attaches to a RayHit: RayHit::new (tracing.rs:121-133), the per-primitive
+// normals (geometry.rs:411,449,478,520), and for meshes geometry.rs:350-363 + 274-298 + 307-309
+template <bool COUNT>
+__device__ __forceinline__ void resolve_hit(const rt_dev_scene& sc, f3 wo, f3 wd, const Best& b, Surface& s,
+                                            unsigned long long* counters) {
+  uint32_t q = (uint32_t)b.obj * RT_OBJ_QUADS;
+  float4 h = ldq(sc.objects, q);
+  int kind = (int)fbits(h.x);
+  int mat = (int)fbits(h.y);
+  uint32_t cls = fbits(h.z);
+  s.u = s.v = 0.0f;
+  bool front;
+  if (kind == RT_OBJ_MESH) {
+    float4 r0 = ldq(sc.objects, q + 1), r1 = ldq(sc.objects, q + 2), r2 = ldq(sc.objects, q + 3);
+    float4 m0 = ldq(sc.objects, q + 4), m1 = ldq(sc.objects, q + 5), m2 = ldq(sc.objects, q + 6);
+    float4 m7 = ldq(sc.objects, q + 7), m8 = ldq(sc.objects, q + 8);
+    f3 o = mk(r0.x * wo.x + r0.y * wo.y + r0.z * wo.z + r0.w * 1.0f, r1.x * wo.x + r1.y * wo.y + r1.z * wo.z + r1.w * 1.0f,
+              r2.x * wo.x + r2.y * wo.y + r2.z * wo.z + r2.w * 1.0f);
+    f3 d = mk(r0.x * wd.x + r0.y * wd.y + r0.z * wd.z + r0.w * 0.0f, r1.x * wd.x + r1.y * wd.y + r1.z * wd.z + r1.w * 0.0f,
+              r2.x * wd.x + r2.y * wd.y + r2.z * wd.z + r2.w * 0.0f);
+    uint32_t sq = (fbits(m7.y) + b.prim) * RT_SHADE_QUADS;
+    float4 s0 = ldq(sc.shade, sq), s1 = ldq(sc.shade, sq + 1), s2 = ldq(sc.shade, sq + 2), s3 = ldq(sc.shade, sq + 3),
+           s4 = ldq(sc.shade, sq + 4);
+    if (COUNT) atomicAdd(&counters[4], 1ull);
+    f3 na = mk(s0.x, s0.y, s0.z), nb = mk(s0.w, s1.x, s1.y), nc = mk(s1.z, s1.w, s2.x);
+    float tau = s2.y, tav = s2.z, tbu = s2.w, tbv = s3.x, tcu = s3.y, tcv = s3.z;
+    f3 tan = mk(s3.w, s4.x, s4.y);
+    float u = b.u, v = b.v, w = 1.0f - u - v;
+    f3 mesh_normal = normalize(u * nb + v * nc + w * na);
+    front = dot(mesh_normal, d) < 0.0f;
+    f3 n = front ? mesh_normal : -mesh_normal;
+    f3 hp_obj = o + d * b.t;
+    s.u = u * tbu + v * tcu + w * tau;
+    s.v = u * tbv + v * tcv + w * tav;
+    int tex_normal = (int)fbits(m8.z);
+    if (tex_normal >= 0) {
+      f3 bitangent = normalize(cross(n, tan));
+      f3 tangent = normalize(cross(bitangent, n));
+      f3 smp = tex_sample(sc, tex_normal, s.u, s.v);
+      if (COUNT) atomicAdd(&counters[5], 1ull);
+      f3 nm = 2.0f * smp - mk(1.0f, 1.0f, 1.0f);
+      n = tangent * nm.x + bitangent * nm.y + n * nm.z;
+    }
+    // inv_transform.transpose().transform_vector(n).normalize(): dot with the columns of inv
+    f3 wn = mk(r0.x * n.x + r1.x * n.y + r2.x * n.z + 0.0f * 0.0f, r0.y * n.x + r1.y * n.y + r2.y * n.z + 0.0f * 0.0f,
+               r0.z * n.x + r1.z * n.y + r2.z * n.z + 0.0f * 0.0f);
+    s.n = normalize(wn);
+    s.hp = mk(m0.x * hp_obj.x + m0.y * hp_obj.y + m0.z * hp_obj.z + m0.w * 1.0f,
+              m1.x * hp_obj.x + m1.y * hp_obj.y + m1.z * hp_obj.z + m1.w * 1.0f,
+              m2.x * hp_obj.x + m2.y * hp_obj.y + m2.z * hp_obj.z + m2.w * 1.0f);
+    uint32_t id = mat >= 0 ? (uint32_t)mat : (uint32_t)b.obj;
+    s.meta = cls | ((front ? 1u : 0u) << 3) | (id << 4);
+    return;
+  }
+  float4 q1 = ldq(sc.objects, q + 1);
+  f3 nrm;
+  s.hp = wo + wd * b.t;
+  if (kind == RT_OBJ_SPHERE) {
+    f3 hitpoint = wo + b.t * wd;
+    nrm = normalize(hitpoint - mk(q1.x, q1.y, q1.z));
+  } else if (kind == RT_OBJ_TRIANGLE) {
+    float4 q3 = ldq(sc.objects, q + 3);
+    nrm = mk(q3.y, q3.z, q3.w);
+  } else if (kind == RT_OBJ_PLANE) {
+    float4 q2 = ldq(sc.objects, q + 2);
+    f3 pn = mk(q2.x, q2.y, q2.z);
+    float od = dot(wo - mk(q1.x, q1.y, q1.z), pn);
+    float sg = (od != od) ? od : (signbit(od) ? -1.0f : 1.0f);
+    nrm = sg * pn;
+  } else {  // volume: zero normal, frontface false (geometry.rs:520)
+    nrm = mk(0.0f, 0.0f, 0.0f);
+  }
+  front = dot(nrm, wd) < 0.0f;
+  s.n = front ? nrm : -nrm;
+  s.meta = cls | ((front ? 1u : 0u) << 3) | ((uint32_t)mat << 4);
+}
+
+// ------------------------------------------------------------------ k_advance
+__global__ void k_advance(rt_ctrl* c, uint32_t capacity) {
+  uint32_t n_cont = c->n_next;
+  unsigned long long remaining = c->total - c->cursor;
+  unsigned long long room = capacity - n_cont;
+  uint32_t n_new = (uint32_t)(remaining < room ? remaining : room);
+  c->n_cont = n_cont;
+  c->n_rays = n_cont + n_new;
+  c->work_base = c->cursor;
+  c->cursor += n_new;
+  c->n_next = 0;
+#pragma unroll
+  for (int i = 0; i < RT_NUM_CLASSES; ++i) c->class_count[i] = 0;
+  if (n_cont + n_new == 0) c->done = 1;
+  else c->iterations += 1;
+}
+
+// ------------------------------------------------------------------ k_extend
+template <bool COUNT, bool DEBUG>
+__global__ void __launch_bounds__(RT_BLOCK) k_extend(rt_dev_scene sc, rt_frame fr, rt_ctrl* __restrict__ ctrl,
+                                                     rt_paths cur, rt_hits hits, uint32_t* __restrict__ queues,
+                                                     rt_debug dbg) {
+  __shared__ uint32_t sstack[RT_SMEM_STACK * RT_BLOCK];
+  __shared__ uint32_t s_wcount[RT_WARPS][RT_NUM_CLASSES];
+  __shared__ uint32_t s_base[RT_NUM_CLASSES];
+  const uint32_t n_rays = ctrl->n_rays, n_cont = ctrl->n_cont;
+  const uint32_t i = blockIdx.x * RT_BLOCK + threadIdx.x;
+  if (blockIdx.x * RT_BLOCK >= n_rays) return;  // whole block idle
+  const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+
+  int cls = -1;
+  if (i < n_rays) {
+    f3 o, d;
+    uint32_t pixel, sb;
+    bool valid = true;
+    if (i < n_cont) {
+      float4 a = cur.A[i], b = cur.B[i];
+      float4 c = cur.C[i];
+      o = mk(a.x, a.y, a.z);
+      d = mk(a.w, b.x, b.y);
+      pixel = fbits(c.y);
+      sb = fbits(c.z);
+    } else {
+      uint32_t x, y, sample;
+      valid = work_to_pixel(fr, ctrl->work_base + (i - n_cont), x, y, sample);
+      pixel = y * fr.width + x;
+      sb = sample;  // bounce 0 in the top byte
+      if (!valid) atomicAdd(&ctrl->counters[7], 1ull);  // tile slot outside the image
+      if (valid) {
+        camera_ray(fr, x, y, pixel, sample, o, d);
+        cur.A[i] = make_float4(o.x, o.y, o.z, d.x);
+        cur.B[i] = make_float4(d.y, d.z, 1.0f, 1.0f);
+        cur.C[i] = make_float4(1.0f, __uint_as_float(pixel), __uint_as_float(sb), 0.0f);
+      }
+    }
+    if (valid) {
+      Best best;
+      Cnt cnt = {0, 0, 0, 0};
+      closest_hit<COUNT>(sc, o, d, fr.t_min, fr.t_max, fr.k0, fr.k1, pixel, sb & 0xFFFFFFu, sb >> 24, sstack, best, cnt);
+      if (COUNT) {
+        atomicAdd(&ctrl->counters[0], (unsigned long long)cnt.nodes);
+        atomicAdd(&ctrl->counters[1], (unsigned long long)cnt.tris);
+        atomicAdd(&ctrl->counters[2], (unsigned long long)cnt.inst);
+        atomicAdd(&ctrl->counters[3], (unsigned long long)cnt.prims);
+      }
+      if (DEBUG) {
+        if (dbg.obj) dbg.obj[i] = best.obj;
+        if (dbg.prim) dbg.prim[i] = best.obj >= 0 ? (int)best.prim : 0;
+        if (dbg.t) dbg.t[i] = best.obj >= 0 ? best.t : 0.0f;
+      }
+      if (best.obj >= 0) {
+        Surface s;
+        resolve_hit<COUNT>(sc, o, d, best, s, ctrl->counters);
+        hits.H0[i] = make_float4(s.hp.x, s.hp.y, s.hp.z, s.n.x);
+        hits.H1[i] = make_float4(s.n.y, s.n.z, s.u, s.v);
+        hits.H2[i] = s.meta;
+        cls = (int)(s.meta & 7u);
+      } else if (DEBUG) {
+        hits.H0[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        hits.H1[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        hits.H2[i] = 0xFFFFFFFFu;
+      }
+    }
+  }
+
+  // material-sorted enqueue: warp match groups -> per-warp counts -> one atomic per class per block
+  if (threadIdx.x < RT_WARPS * RT_NUM_CLASSES) (&s_wcount[0][0])[threadIdx.x] = 0;
+  __syncthreads();
+  uint32_t rank = 0;
+  {
+    uint32_t peers = __match_any_sync(0xFFFFFFFFu, cls);
+    rank = __popc(peers & ((1u << lane) - 1u));
+    if (cls >= 0 && rank == 0) s_wcount[warp][cls] = __popc(peers);
+  }
+  __syncthreads();
+  if (threadIdx.x < RT_NUM_CLASSES) {
+    uint32_t total = 0;
+#pragma unroll
+    for (int w = 0; w < RT_WARPS; ++w) {
+      uint32_t c = s_wcount[w][threadIdx.x];
+      s_wcount[w][threadIdx.x] = total;  // exclusive prefix over warps
+      total += c;
+    }
+    s_base[threadIdx.x] = total ? atomicAdd(&ctrl->class_count[threadIdx.x], total) : 0u;
+  }
+  __syncthreads();
+  if (cls >= 0) queues[(size_t)cls * fr.capacity + s_base[cls] + s_wcount[warp][cls] + rank] = i;
+}
+
+// ------------------------------------------------------------------ materials
+__device__ __forceinline__ f3 reflectv(f3 v, f3 n) { return v - 2.0f * dot(v, n) * n; }  // tracing.rs:54-56
+__device__ __forceinline__ float fresnelf(f3 v, f3 n, float ir) {                         // tracing.rs:58-62
+  float q = (ir - 1.0f) / (ir + 1.0f);
+  float r0 = q * q;
+  float x = 1.0f - fabsf(dot(v, n));
+  float x2 = x * x;
+  return r0 + (1.0f - r0) * (x * (x2 * x2));
+}
+__device__ __forceinline__ f3 refractv(f3 v, f3 n, float eta) {  // tracing.rs:64-69
+  float cos_theta = fminf(dot(-v, n), 1.0f);
+  f3 perp = eta * (v + cos_theta * n);
+  f3 par = -sqrtf(fabsf(1.0f - mag2(perp))) * n;
+  return perp + par;
+}
+__device__ __forceinline__ bool ulps_eq(float a, float b) {  // approx::ulps_eq!, epsilon = EPSILON, 4 ulps
+  if (fabsf(a - b) <= 1.1920929e-7f) return true;
+  if (signbit(a) != signbit(b)) return false;
+  long long d = (long long)__float_as_int(a) - (long long)__float_as_int(b);
+  return (d < 0 ? -d : d) <= 4;
+}
+// sample_hemisphere, materials.rs:171-178: ball with y=|y|, rotated by Quaternion::from_arc(unit_y, n)
+__device__ __forceinline__ f3 sample_hemisphere(f3 n, f3 ball) {
+  f3 dir = mk(ball.x, fabsf(ball.y), ball.z);
+  float mag_avg = sqrtf(1.0f * mag2(n));
+  float dt = 0.0f * n.x + 1.0f * n.y + 0.0f * n.z;  // dot(unit_y, n)
+  float s;
+  f3 v;
+  if (ulps_eq(dt, mag_avg)) return dir;
+  if (ulps_eq(dt, -mag_avg)) {
+    s = -4.371139e-8f;
+    v = mk(0.0f, 0.0f, 1.0f);
+  } else {
+    s = mag_avg + dt;
+    v = cross(mk(0.0f, 1.0f, 0.0f), n);
+    float inv = 1.0f / sqrtf(s * s + mag2(v));
+    s = s * inv;
+    v = v * inv;
+  }
+  f3 tmp = cross(v, dir) + dir * s;
+  return cross(v, tmp) * 2.0f + dir;
+}
+
+// fixed-point accumulation (2^-30 units): order-independent, hence reproducible and shardable
+#define RT_FIX_SCALE 1073741824.0f
+#define RT_FIX_CLAMP 65536.0f
+__device__ __forceinline__ void accum_add(long long* accum, uint32_t pixel, f3 c) {
+  float v[3] = {c.x, c.y, c.z};
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    float x = v[k];
+    if (x != x) {
+      atomicAdd(reinterpret_cast<unsigned long long*>(accum + (size_t)pixel * 4 + 3), 1ull << (21 * k));
+    } else if (x != 0.0f) {
+      x = fminf(fmaxf(x, -RT_FIX_CLAMP), RT_FIX_CLAMP);
+      long long q = __float2ll_rn(x * RT_FIX_SCALE);
+      atomicAdd(reinterpret_cast<unsigned long long*>(accum + (size_t)pixel * 4 + k), (unsigned long long)q);
+    }
+  }
+}
+
+// ------------------------------------------------------------------ k_shade
+template <bool COUNT>
+__global__ void __launch_bounds__(RT_BLOCK) k_shade(rt_dev_scene sc, rt_frame fr, rt_ctrl* __restrict__ ctrl,
+                                                    rt_paths cur, rt_paths nxt, rt_hits hits,
+                                                    const uint32_t* __restrict__ queues, long long* __restrict__ accum) {
+  __shared__ uint32_t s_wcount[RT_WARPS];
+  __shared__ uint32_t s_base;
+  // which class does this block serve?  class segments are padded to whole blocks
+  uint32_t b = blockIdx.x;
+  int cls = -1;
+  uint32_t count = 0;
+#pragma unroll
+  for (int c = 0; c < RT_NUM_CLASSES; ++c) {
+    uint32_t n = ctrl->class_count[c];
+    uint32_t nb = (n + RT_BLOCK - 1) / RT_BLOCK;
+    if (cls < 0) {
+      if (b < nb) {
+        cls = c;
+        count = n;
+      } else {
+        b -= nb;
+      }
+    }
+  }
+  if (cls < 0) return;
+  const uint32_t j = b * RT_BLOCK + threadIdx.x;
+  const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+
+  bool alive = false;
+  f3 no, nd, nT;
+  uint32_t pixel = 0, sb = 0;
+  if (j < count) {
+    uint32_t slot = queues[(size_t)cls * fr.capacity + j];
+    float4 a = cur.A[slot], bq = cur.B[slot], c = cur.C[slot];
+    float4 h0 = hits.H0[slot], h1 = hits.H1[slot];
+    uint32_t meta = hits.H2[slot];
+    f3 d = mk(a.w, bq.x, bq.y);
+    f3 T = mk(bq.z, bq.w, c.x);
+    pixel = fbits(c.y);
+    sb = fbits(c.z);
+    uint32_t sample = sb & 0xFFFFFFu, bounce = sb >> 24;
+    f3 hp = mk(h0.x, h0.y, h0.z), n = mk(h0.w, h1.x, h1.y);
+    bool front = (meta >> 3) & 1u;
+    uint32_t id = meta >> 4;
+
+    // material parameters
+    f3 albedo, emission;
+    float roughness, metallic;
+    if (cls == RT_CLASS_PARAM_TEX) {
+      // StaticMesh::get_material_at_uv, geometry.rs:259-269 (Q7 defaults)
+      uint32_t q = id * RT_OBJ_QUADS;
+      float4 m7 = ldq(sc.objects, q + 7), m8 = ldq(sc.objects, q + 8);
+      int ta = (int)fbits(m7.z), te = (int)fbits(m7.w), tm = (int)fbits(m8.x), tr = (int)fbits(m8.y);
+      float u = h1.z, v = h1.w;
+      albedo = ta >= 0 ? tex_sample(sc, ta, u, v) : mk(0.f, 0.f, 0.f);
+      emission = te >= 0 ? tex_sample(sc, te, u, v) : mk(0.f, 0.f, 0.f);
+      metallic = tm >= 0 ? tex_sample(sc, tm, u, v).x : 0.0f;
+      roughness = tr >= 0 ? tex_sample(sc, tr, u, v).x : 1.0f;
+      if (COUNT) atomicAdd(&ctrl->counters[5], (unsigned long long)((ta >= 0) + (te >= 0) + (tm >= 0) + (tr >= 0)));
+    } else {
+      float4 m0 = ldq(sc.mats, id * RT_MAT_QUADS), m1 = ldq(sc.mats, id * RT_MAT_QUADS + 1);
+      if (COUNT) atomicAdd(&ctrl->counters[6], 1ull);
+      albedo = mk(m0.x, m0.y, m0.z);
+      emission = mk(m1.x, m1.y, m1.z);
+      roughness = m0.w;
+      metallic = m1.w;
+    }
+
+    // emitted light reaches the pixel attenuated by the path throughput (tracing.rs:321)
+    if (emission.x != 0.0f || emission.y != 0.0f || emission.z != 0.0f) accum_add(accum, pixel, mulv(T, emission));
+
+    // scatter (materials.rs:33-166)
+    u4 r = philox4x32_10(pixel, sample, bounce, 0u, fr.k0, fr.k1);
+    float u_choice = u01(r.x);
+    f3 ball = ball_from(r.y, r.z, r.w);
+    f3 dir, brdf;
+    float pdf;
+    const float PI = RT_PI;
+    if (cls == RT_CLASS_LAMBERT) {
+      dir = sample_hemisphere(n, ball);
+      brdf = albedo / PI;
+      pdf = 1.0f / (2.0f * PI);
+    } else if (cls == RT_CLASS_METAL) {
+      dir = reflectv(d, n) + roughness * ball;
+      brdf = albedo;
+      pdf = 1.0f;
+    } else if (cls == RT_CLASS_DIELECTRIC) {
+      float ior = roughness;  // stored in the roughness slot
+      float eta = front ? 1.0f / ior : ior;
+      float cth = fminf(-dot(d, n), 1.0f);
+      bool critical = eta * sqrtf(1.0f - cth * cth) > 1.0f;
+      float fres = fresnelf(d, n, ior);
+      bool will_refract = !critical && u_choice >= fres;
+      dir = will_refract ? refractv(d, n, eta) : reflectv(d, n);
+      brdf = mk(1.0f, 1.0f, 1.0f);
+      pdf = 1.0f;
+    } else if (cls == RT_CLASS_ISOTROPIC) {
+      dir = ball;
+      brdf = albedo;
+      pdf = 1.0f;
+    } else {  // PARAM / PARAM_TEX, materials.rs:114-145
+      float fres = fresnelf(d, n, 1.5f);
+      float k_s = fres * (1.0f - roughness);
+      float k_d = (1.0f - k_s) * (1.0f - metallic);
+      if (u_choice < k_d) {
+        dir = sample_hemisphere(n, ball);
+        brdf = albedo / PI;
+        pdf = 1.0f / (2.0f * PI);
+      } else {
+        dir = reflectv(d, n) + roughness * ball;
+        brdf = (1.0f - metallic) * mk(1.0f, 1.0f, 1.0f) + metallic * albedo;  // lerpvec(1, albedo, metallic)
+        pdf = 1.0f;
+      }
+    }
+    // tracing.rs:313-316
+    float dot_term = mag2(n) > 0.0f ? clampf(fabsf(dot(dir, n)), 0.0f, 1.0f) : 1.0f;
+    f3 w = (dot_term * brdf) / pdf;
+    nT = mulv(T, w);
+    no = hp;
+    nd = dir;
+    bounce += 1;
+    sb = sample | (bounce << 24);
+    // the next segment exists only below path_depth (tracing.rs:301); a path whose throughput is
+    // exactly zero can add nothing any more
+    alive = bounce < fr.path_depth && !(nT.x == 0.0f && nT.y == 0.0f && nT.z == 0.0f);
+  }
+
+  // compact survivors into the next ray queue: ballot per warp, one atomic per block
+  uint32_t bal = __ballot_sync(0xFFFFFFFFu, alive);
+  if (lane == 0) s_wcount[warp] = __popc(bal);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    uint32_t total = 0;
+#pragma unroll
+    for (int w = 0; w < RT_WARPS; ++w) {
+      uint32_t c = s_wcount[w];
+      s_wcount[w] = total;
+      total += c;
+    }
+    s_base = total ? atomicAdd(&ctrl->n_next, total) : 0u;
+  }
+  __syncthreads();
+  if (alive) {
+    uint32_t pos = s_base + s_wcount[warp] + __popc(bal & ((1u << lane) - 1u));
+    nxt.A[pos] = make_float4(no.x, no.y, no.z, nd.x);
+    nxt.B[pos] = make_float4(nd.y, nd.z, nT.x, nT.y);
+    nxt.C[pos] = make_float4(nT.z, __uint_as_float(pixel), __uint_as_float(sb), 0.0f);
+  }
+}
+
+// ------------------------------------------------------------------ k_resolve (Q12)
+__global__ void k_resolve(const long long* __restrict__ accum, uint32_t npix, uint32_t spp, float gamma,
+                          float* __restrict__ out_linear, uint8_t* __restrict__ out_rgb8) {
+  uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= npix) return;
+  const longlong2* a = reinterpret_cast<const longlong2*>(accum + (size_t)p * 4);
+  longlong2 rg = a[0], bn = a[1];
+  unsigned long long nan = (unsigned long long)bn.y;
+  float c[3];
+  long long s[3] = {rg.x, rg.y, bn.x};
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    float sum = (float)((double)s[k] * (1.0 / 1073741824.0));
+    if ((nan >> (21 * k)) & 0x1FFFFFull) sum = CUDART_NAN_F;
+    c[k] = sum / (float)spp;  // tracing.rs:241
+  }
+  if (out_linear) {
+    out_linear[(size_t)p * 3 + 0] = c[0];
+    out_linear[(size_t)p * 3 + 1] = c[1];
+    out_linear[(size_t)p * 3 + 2] = c[2];
+  }
+  if (out_rgb8) {
+    float f[3] = {c[0], c[1], c[2]};
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {  // tracing.rs:244-251, reads the pre-update copy
+      float d = c[k] - 1.0f;
+      if (d > 0.0f) {
+        f[(k + 1) % 3] += d;
+        f[(k + 2) % 3] += d;
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      float v = powf(clampf(f[k], 0.0f, 1.0f), 1.0f / gamma) * 255.9999f;
+      out_rgb8[(size_t)p * 3 + k] = (v != v || v <= 0.0f) ? 0 : (v >= 255.0f ? 255 : (uint8_t)v);
+    }
+  }
+}
+
+__global__ void k_init_ctrl(rt_ctrl* c, unsigned long long total) {
+  c->cursor = 0;
+  c->total = total;
+  c->n_samples = 0;
+  c->n_rays_total = 0;
+  c->n_cont = 0;
+  c->n_rays = 0;
+  c->work_base = 0;
+  c->n_next = 0;
+  for (int i = 0; i < RT_NUM_CLASSES; ++i) c->class_count[i] = 0;
+  c->done = 0;
+  c->iterations = 0;
+  for (int i = 0; i < 8; ++i) c->counters[i] = 0;
+}
+// stats that k_advance cannot see until the iteration has run
+__global__ void k_tally(rt_ctrl* c) {
+  c->n_rays_total += c->n_rays;
+  c->n_samples += c->n_rays - c->n_cont;
+}
+
+// ------------------------------------------------------------------ launchers
+void launch_init(rt_ctrl* ctrl, unsigned long long total, cudaStream_t st) { k_init_ctrl<<<1, 1, 0, st>>>(ctrl, total); }
+void launch_advance(rt_ctrl* ctrl, uint32_t capacity, cudaStream_t st) {
+  k_advance<<<1, 1, 0, st>>>(ctrl, capacity);
+  k_tally<<<1, 1, 0, st>>>(ctrl);
+}
+void launch_extend(const rt_dev_scene& sc, const rt_frame& fr, rt_ctrl* ctrl, rt_paths cur, rt_hits hits,
+                   uint32_t* queues, rt_debug dbg, bool count, bool debug, cudaStream_t st) {
+  uint32_t grid = (fr.capacity + RT_BLOCK - 1) / RT_BLOCK;
+  if (debug) {
+    if (count) k_extend<true, true><<<grid, RT_BLOCK, 0, st>>>(sc, fr, ctrl, cur, hits, queues, dbg);
+    else k_extend<false, true><<<grid, RT_BLOCK, 0, st>>>(sc, fr, ctrl, cur, hits, queues, dbg);
+  } else {
+    if (count) k_extend<true, false><<<grid, RT_BLOCK, 0, st>>>(sc, fr, ctrl, cur, hits, queues, dbg);
+    else k_extend<false, false><<<grid, RT_BLOCK, 0, st>>>(sc, fr, ctrl, cur, hits, queues, dbg);
+  }
+}
+void launch_shade(const rt_dev_scene& sc, const rt_frame& fr, rt_ctrl* ctrl, rt_paths cur, rt_paths nxt, rt_hits hits,
+                  const uint32_t* queues, long long* accum, bool count, cudaStream_t st) {
+  uint32_t grid = (fr.capacity + RT_BLOCK - 1) / RT_BLOCK + RT_NUM_CLASSES;
+  if (count) k_shade<true><<<grid, RT_BLOCK, 0, st>>>(sc, fr, ctrl, cur, nxt, hits, queues, accum);
+  else k_shade<false><<<grid, RT_BLOCK, 0, st>>>(sc, fr, ctrl, cur, nxt, hits, queues, accum);
+}
+void launch_resolve(const long long* accum, uint32_t npix, uint32_t spp, float gamma, float* out_linear,
+                    uint8_t* out_rgb8, cudaStream_t st) {
+  k_resolve<<<(npix + 255) / 256, 256, 0, st>>>(accum, npix, spp, gamma, out_linear, out_rgb8);
+}
+
+}  // namespace rt

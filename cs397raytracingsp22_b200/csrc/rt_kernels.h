@@ -1,0 +1,42 @@
+// rt_kernels.h — launch interface between the C ABI (rt_api.cu) and the kernels (rt_kernels.cu).
+#ifndef RT_KERNELS_H
+#define RT_KERNELS_H
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/rt_b200.h"
+#include "rt_types.h"
+
+namespace rt {
+
+// ray queue, SoA of quads (48 B per path): A=(o.xyz,d.x) B=(d.yz,T.x,T.y) C=(T.z,pixel,sample|bounce<<24,_)
+struct rt_paths {
+  float4* A;
+  float4* B;
+  float4* C;
+};
+// hit records written by k_extend for k_shade (36 B per ray): H0=(hitpoint.xyz,n.x) H1=(n.yz,u,v) H2=meta
+struct rt_hits {
+  float4* H0;
+  float4* H1;
+  uint32_t* H2;
+};
+// parity hooks only
+struct rt_debug {
+  int32_t* obj;
+  int32_t* prim;
+  float* t;
+};
+
+void launch_init(rt_ctrl* ctrl, unsigned long long total, cudaStream_t st);
+void launch_advance(rt_ctrl* ctrl, uint32_t capacity, cudaStream_t st);
+void launch_extend(const rt_dev_scene& sc, const rt_frame& fr, rt_ctrl* ctrl, rt_paths cur, rt_hits hits,
+                   uint32_t* queues, rt_debug dbg, bool count, bool debug, cudaStream_t st);
+void launch_shade(const rt_dev_scene& sc, const rt_frame& fr, rt_ctrl* ctrl, rt_paths cur, rt_paths nxt, rt_hits hits,
+                  const uint32_t* queues, long long* accum, bool count, cudaStream_t st);
+void launch_resolve(const long long* accum, uint32_t npix, uint32_t spp, float gamma, float* out_linear,
+                    uint8_t* out_rgb8, cudaStream_t st);
+
+}  // namespace rt
+#endif

@@ -1,0 +1,803 @@
+// rt_lower.cpp — host lowering: reference-reachability mask, binned-SAH BVH2 (32-byte nodes,
+// children in adjacent pairs), leaf-packed triangle records, TLAS over bounded objects,
+// tagged-union material / texture tables; plus the asset readers (OBJ, TGA).
+//
+// Must be compiled WITHOUT floating-point contraction (-ffp-contract=off): the records
+// precomputed here (edges, tangents, normals) have to be bit-identical to what the
+// reference computes per ray (geometry.rs:336-337,245-250,449).
+
+#include "rt_lower.h"
+
+#include <algorithm>
+#include <cfloat>
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
+#include <unordered_map>
+
+namespace rt {
+
+// ------------------------------------------------------------------ small helpers
+static inline float fmin3(float a, float b, float c) { return std::fmin(a, std::fmin(b, c)); }
+static inline float fmax3(float a, float b, float c) { return std::fmax(a, std::fmax(b, c)); }
+
+uint64_t Lowered::bytes() const {
+  return (nodes.size() + tris.size() + shade.size() + objects.size() + mats.size() + textures.size()) * 16ull +
+         texels.size() * 4ull + planes.size() * 4ull;
+}
+
+// ------------------------------------------------------------------ reachability (Q3)
+// The reference tree (geometry.rs:190-217): node over [start,end), mid = start+(end-start)/2,
+// leaf = triangle `start`.  Its slab test (geometry.rs:63-67) rejects when tmax <= tmin, so an
+// INTERIOR node whose box has zero thickness on an axis is never entered, and every triangle
+// below it can never be hit.  Leaves are not box-tested (geometry.rs:95-98).
+namespace {
+struct Box3 {
+  float mn[3], mx[3];
+};
+Box3 reach_rec(const float* pos, const uint32_t* idx, uint32_t start, uint32_t end, bool dead, uint8_t* mask) {
+  Box3 b;
+  if (end - start == 1) {
+    const float* a = pos + 3 * (size_t)idx[3 * start];
+    const float* p = pos + 3 * (size_t)idx[3 * start + 1];
+    const float* c = pos + 3 * (size_t)idx[3 * start + 2];
+    for (int k = 0; k < 3; ++k) {
+      b.mn[k] = fmin3(a[k], p[k], c[k]);
+      b.mx[k] = fmax3(a[k], p[k], c[k]);
+    }
+    mask[start] = dead ? 0 : 1;
+    return b;
+  }
+  uint32_t mid = start + (end - start) / 2;
+  // boxes first (bottom-up), then decide flatness; children inherit `dead` afterwards
+  Box3 l = reach_rec(pos, idx, start, mid, dead, mask);
+  Box3 r = reach_rec(pos, idx, mid, end, dead, mask);
+  for (int k = 0; k < 3; ++k) {
+    b.mn[k] = std::fmin(l.mn[k], r.mn[k]);
+    b.mx[k] = std::fmax(l.mx[k], r.mx[k]);
+  }
+  bool flat = b.mn[0] == b.mx[0] || b.mn[1] == b.mx[1] || b.mn[2] == b.mx[2];
+  if (flat && !dead)
+    for (uint32_t t = start; t < end; ++t) mask[t] = 0;
+  return b;
+}
+}  // namespace
+
+void mesh_reachability(const float* pos, const uint32_t* idx, uint32_t ntris, uint8_t* mask) {
+  if (ntris == 0) return;
+  reach_rec(pos, idx, 0, ntris, false, mask);
+}
+
+// ------------------------------------------------------------------ binned SAH BVH2
+namespace {
+struct BPrim {
+  float mn[3], mx[3], c[3];
+  uint32_t id;
+};
+struct BNode {
+  float mn[3], mx[3];
+  uint32_t leftFirst, count;
+};
+inline float half_area(const float* mn, const float* mx) {
+  float ex = mx[0] - mn[0], ey = mx[1] - mn[1], ez = mx[2] - mn[2];
+  return ex * ey + ey * ez + ez * ex;
+}
+
+void subdivide(std::vector<BPrim>& prims, std::vector<BNode>& nodes, uint32_t ni, uint32_t max_leaf) {
+  const int NB = 16;
+  uint32_t first = nodes[ni].leftFirst, count = nodes[ni].count;
+  // bounds
+  float mn[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, mx[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
+  float cmn[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, cmx[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
+  for (uint32_t i = first; i < first + count; ++i)
+    for (int k = 0; k < 3; ++k) {
+      mn[k] = std::min(mn[k], prims[i].mn[k]);
+      mx[k] = std::max(mx[k], prims[i].mx[k]);
+      cmn[k] = std::min(cmn[k], prims[i].c[k]);
+      cmx[k] = std::max(cmx[k], prims[i].c[k]);
+    }
+  for (int k = 0; k < 3; ++k) {
+    nodes[ni].mn[k] = mn[k];
+    nodes[ni].mx[k] = mx[k];
+  }
+  if (count <= 1) return;
+
+  int best_axis = -1, best_bin = -1;
+  float best_cost = FLT_MAX;
+  for (int axis = 0; axis < 3; ++axis) {
+    float ext = cmx[axis] - cmn[axis];
+    if (!(ext > 0.0f)) continue;
+    struct Bin {
+      float mn[3], mx[3];
+      uint32_t n;
+    } bins[NB];
+    for (auto& b : bins) {
+      b.n = 0;
+      for (int k = 0; k < 3; ++k) {
+        b.mn[k] = FLT_MAX;
+        b.mx[k] = -FLT_MAX;
+      }
+    }
+    float scale = (float)NB / ext;
+    for (uint32_t i = first; i < first + count; ++i) {
+      int bi = std::min(NB - 1, (int)((prims[i].c[axis] - cmn[axis]) * scale));
+      Bin& b = bins[bi];
+      b.n++;
+      for (int k = 0; k < 3; ++k) {
+        b.mn[k] = std::min(b.mn[k], prims[i].mn[k]);
+        b.mx[k] = std::max(b.mx[k], prims[i].mx[k]);
+      }
+    }
+    float la[NB - 1], ra[NB - 1];
+    uint32_t ln[NB - 1], rn[NB - 1];
+    float amn[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, amx[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
+    uint32_t acc = 0;
+    for (int i = 0; i < NB - 1; ++i) {
+      acc += bins[i].n;
+      for (int k = 0; k < 3; ++k) {
+        amn[k] = std::min(amn[k], bins[i].mn[k]);
+        amx[k] = std::max(amx[k], bins[i].mx[k]);
+      }
+      ln[i] = acc;
+      la[i] = acc ? half_area(amn, amx) : 0.0f;
+    }
+    for (int k = 0; k < 3; ++k) {
+      amn[k] = FLT_MAX;
+      amx[k] = -FLT_MAX;
+    }
+    acc = 0;
+    for (int i = NB - 1; i > 0; --i) {
+      acc += bins[i].n;
+      for (int k = 0; k < 3; ++k) {
+        amn[k] = std::min(amn[k], bins[i].mn[k]);
+        amx[k] = std::max(amx[k], bins[i].mx[k]);
+      }
+      rn[i - 1] = acc;
+      ra[i - 1] = acc ? half_area(amn, amx) : 0.0f;
+    }
+    for (int i = 0; i < NB - 1; ++i) {
+      if (ln[i] == 0 || rn[i] == 0) continue;
+      float cost = la[i] * (float)ln[i] + ra[i] * (float)rn[i];
+      if (cost < best_cost) {
+        best_cost = cost;
+        best_axis = axis;
+        best_bin = i;
+      }
+    }
+  }
+
+  float parent_area = half_area(mn, mx);
+  bool must_split = count > max_leaf;
+  // cost model: one node-pair visit ~ one triangle test
+  bool sah_split = best_axis >= 0 && (best_cost + parent_area) < parent_area * (float)count;
+  if (!must_split && !sah_split) return;
+
+  uint32_t mid;
+  if (best_axis >= 0) {
+    float ext = cmx[best_axis] - cmn[best_axis];
+    float scale = (float)NB / ext;
+    auto it = std::partition(prims.begin() + first, prims.begin() + first + count, [&](const BPrim& p) {
+      int bi = std::min(NB - 1, (int)((p.c[best_axis] - cmn[best_axis]) * scale));
+      return bi <= best_bin;
+    });
+    mid = (uint32_t)(it - prims.begin());
+  } else {
+    mid = first;  // all centroids coincide
+  }
+  if (mid == first || mid == first + count) {
+    // fall back to an object median split along the widest axis (keeps ids ascending otherwise)
+    int axis = 0;
+    float e0 = mx[0] - mn[0], e1 = mx[1] - mn[1], e2 = mx[2] - mn[2];
+    if (e1 > e0 && e1 >= e2) axis = 1;
+    if (e2 > e0 && e2 > e1) axis = 2;
+    mid = first + count / 2;
+    std::nth_element(prims.begin() + first, prims.begin() + mid, prims.begin() + first + count,
+                     [axis](const BPrim& a, const BPrim& b) {
+                       return a.c[axis] < b.c[axis] || (a.c[axis] == b.c[axis] && a.id < b.id);
+                     });
+  }
+  uint32_t left = (uint32_t)nodes.size();
+  nodes.push_back(BNode{});
+  nodes.push_back(BNode{});
+  nodes[left].leftFirst = first;
+  nodes[left].count = mid - first;
+  nodes[left + 1].leftFirst = mid;
+  nodes[left + 1].count = first + count - mid;
+  nodes[ni].leftFirst = left;
+  nodes[ni].count = 0;
+  subdivide(prims, nodes, left, max_leaf);
+  subdivide(prims, nodes, left + 1, max_leaf);
+}
+
+// nodes[0] = root, nodes[1] = padding so that child pairs start on even indices (64-byte pairs)
+void build_bvh(std::vector<BPrim>& prims, uint32_t max_leaf, std::vector<BNode>& nodes) {
+  nodes.clear();
+  nodes.reserve(2 * prims.size() + 2);
+  BNode root{};
+  root.leftFirst = 0;
+  root.count = (uint32_t)prims.size();
+  nodes.push_back(root);
+  nodes.push_back(BNode{});
+  for (int k = 0; k < 3; ++k) nodes[1].mn[k] = nodes[1].mx[k] = 0.0f;
+  if (!prims.empty()) subdivide(prims, nodes, 0, max_leaf);
+}
+
+inline uint32_t pack_entry(uint32_t leftFirst, uint32_t count) {
+  return count ? (RT_LEAF_FLAG | (leftFirst << 4) | count) : leftFirst;
+}
+
+void nodes_to_quads(const std::vector<BNode>& nodes, float pad, std::vector<Quad>& out) {
+  out.resize(nodes.size() * 2);
+  for (size_t i = 0; i < nodes.size(); ++i) {
+    Quad lo, hi;
+    for (int k = 0; k < 3; ++k) {
+      lo.f[k] = nodes[i].mn[k] - pad;
+      hi.f[k] = nodes[i].mx[k] + pad;
+    }
+    lo.u[3] = nodes[i].leftFirst;
+    hi.u[3] = nodes[i].count;
+    out[2 * i] = lo;
+    out[2 * i + 1] = hi;
+  }
+}
+}  // namespace
+
+// ------------------------------------------------------------------ mesh -> BLAS + records
+void build_mesh(HostMesh& m) {
+  const uint32_t nt = m.ntris();
+  m.reach.assign(nt, 1);
+  mesh_reachability(m.pos.data(), m.idx.data(), nt, m.reach.data());
+
+  // shading records, original order (geometry.rs:230-250,350-363)
+  m.shade.assign((size_t)nt * RT_SHADE_QUADS, Quad{});
+  std::vector<BPrim> prims;
+  prims.reserve(nt);
+  float amax = 0.0f;
+  for (uint32_t t = 0; t < nt; ++t) {
+    uint32_t i0 = m.idx[3 * t], i1 = m.idx[3 * t + 1], i2 = m.idx[3 * t + 2];
+    const float *pa = &m.pos[3 * (size_t)i0], *pb = &m.pos[3 * (size_t)i1], *pc = &m.pos[3 * (size_t)i2];
+    const float *na = &m.nrm[3 * (size_t)i0], *nb = &m.nrm[3 * (size_t)i1], *nc = &m.nrm[3 * (size_t)i2];
+    const float *ta = &m.uv[2 * (size_t)i0], *tb = &m.uv[2 * (size_t)i1], *tc = &m.uv[2 * (size_t)i2];
+    // StaticMesh::get_tangent, geometry.rs:245-250
+    float u1 = ta[0], u2 = tb[0], u3 = tc[0], v1 = ta[1], v2 = tb[1], v3 = tc[1];
+    float den = (u2 - u1) * (v3 - v1) - (v2 - v1) * (u3 - u1);
+    float tan[3];
+    for (int k = 0; k < 3; ++k) tan[k] = ((v3 - v1) * (pb[k] - pa[k]) - (v2 - v1) * (pc[k] - pa[k])) / den;
+    float rec[20] = {na[0], na[1], na[2], nb[0], nb[1], nb[2], nc[0], nc[1], nc[2], ta[0],
+                     ta[1], tb[0], tb[1], tc[0], tc[1], tan[0], tan[1], tan[2], 0.0f, 0.0f};
+    std::memcpy(&m.shade[(size_t)t * RT_SHADE_QUADS], rec, sizeof rec);
+    if (!m.reach[t]) continue;
+    BPrim p;
+    for (int k = 0; k < 3; ++k) {
+      p.mn[k] = fmin3(pa[k], pb[k], pc[k]);
+      p.mx[k] = fmax3(pa[k], pb[k], pc[k]);
+      p.c[k] = 0.5f * (p.mn[k] + p.mx[k]);
+      amax = std::max(amax, std::max(std::fabs(p.mn[k]), std::fabs(p.mx[k])));
+    }
+    p.id = t;
+    prims.push_back(p);
+  }
+  m.n_reachable = (uint32_t)prims.size();
+
+  std::vector<BNode> nodes;
+  build_bvh(prims, 4, nodes);
+  // Conservative traversal: boxes are padded by a few ulps of the largest coordinate so that a
+  // triangle the reference's Möller–Trumbore test accepts is never culled by rounding in the
+  // slab test (flat boxes of coplanar triangles get thickness this way, cf. Q3).
+  float pad = 4e-6f * amax + 1e-30f;
+  nodes_to_quads(nodes, pad, m.nodes);
+  for (int k = 0; k < 3; ++k) {
+    m.root_min[k] = prims.empty() ? 0.0f : nodes[0].mn[k] - pad;
+    m.root_max[k] = prims.empty() ? 0.0f : nodes[0].mx[k] + pad;
+  }
+  m.root_entry_local = prims.empty() ? RT_ENTRY_NONE : pack_entry(nodes[0].leftFirst, nodes[0].count);
+
+  // intersection records in leaf order: v0, e1 = b - a, e2 = c - a (geometry.rs:336-337), id
+  m.tris.assign(prims.size() * RT_TRI_QUADS, Quad{});
+  for (size_t i = 0; i < prims.size(); ++i) {
+    uint32_t t = prims[i].id;
+    uint32_t i0 = m.idx[3 * t], i1 = m.idx[3 * t + 1], i2 = m.idx[3 * t + 2];
+    const float *pa = &m.pos[3 * (size_t)i0], *pb = &m.pos[3 * (size_t)i1], *pc = &m.pos[3 * (size_t)i2];
+    Quad* q = &m.tris[i * RT_TRI_QUADS];
+    q[0].f[0] = pa[0]; q[0].f[1] = pa[1]; q[0].f[2] = pa[2];
+    q[0].f[3] = pb[0] - pa[0];
+    q[1].f[0] = pb[1] - pa[1]; q[1].f[1] = pb[2] - pa[2];
+    q[1].f[2] = pc[0] - pa[0]; q[1].f[3] = pc[1] - pa[1];
+    q[2].f[0] = pc[2] - pa[2];
+    q[2].u[1] = t;
+    q[2].u[2] = 0; q[2].u[3] = 0;
+  }
+}
+
+// ------------------------------------------------------------------ matrices
+// general 4x4 inverse by cofactors (what cgmath's Matrix4::invert does), f32
+bool invert_affine_cofactor(const float m[16], float out[16]) {
+  float inv[16];
+  inv[0] = m[5] * m[10] * m[15] - m[5] * m[11] * m[14] - m[9] * m[6] * m[15] + m[9] * m[7] * m[14] + m[13] * m[6] * m[11] - m[13] * m[7] * m[10];
+  inv[4] = -m[4] * m[10] * m[15] + m[4] * m[11] * m[14] + m[8] * m[6] * m[15] - m[8] * m[7] * m[14] - m[12] * m[6] * m[11] + m[12] * m[7] * m[10];
+  inv[8] = m[4] * m[9] * m[15] - m[4] * m[11] * m[13] - m[8] * m[5] * m[15] + m[8] * m[7] * m[13] + m[12] * m[5] * m[11] - m[12] * m[7] * m[9];
+  inv[12] = -m[4] * m[9] * m[14] + m[4] * m[10] * m[13] + m[8] * m[5] * m[14] - m[8] * m[6] * m[13] - m[12] * m[5] * m[10] + m[12] * m[6] * m[9];
+  inv[1] = -m[1] * m[10] * m[15] + m[1] * m[11] * m[14] + m[9] * m[2] * m[15] - m[9] * m[3] * m[14] - m[13] * m[2] * m[11] + m[13] * m[3] * m[10];
+  inv[5] = m[0] * m[10] * m[15] - m[0] * m[11] * m[14] - m[8] * m[2] * m[15] + m[8] * m[3] * m[14] + m[12] * m[2] * m[11] - m[12] * m[3] * m[10];
+  inv[9] = -m[0] * m[9] * m[15] + m[0] * m[11] * m[13] + m[8] * m[1] * m[15] - m[8] * m[3] * m[13] - m[12] * m[1] * m[11] + m[12] * m[3] * m[9];
+  inv[13] = m[0] * m[9] * m[14] - m[0] * m[10] * m[13] - m[8] * m[1] * m[14] + m[8] * m[2] * m[13] + m[12] * m[1] * m[10] - m[12] * m[2] * m[9];
+  inv[2] = m[1] * m[6] * m[15] - m[1] * m[7] * m[14] - m[5] * m[2] * m[15] + m[5] * m[3] * m[14] + m[13] * m[2] * m[7] - m[13] * m[3] * m[6];
+  inv[6] = -m[0] * m[6] * m[15] + m[0] * m[7] * m[14] + m[4] * m[2] * m[15] - m[4] * m[3] * m[14] - m[12] * m[2] * m[7] + m[12] * m[3] * m[6];
+  inv[10] = m[0] * m[5] * m[15] - m[0] * m[7] * m[13] - m[4] * m[1] * m[15] + m[4] * m[3] * m[13] + m[12] * m[1] * m[7] - m[12] * m[3] * m[5];
+  inv[14] = -m[0] * m[5] * m[14] + m[0] * m[6] * m[13] + m[4] * m[1] * m[14] - m[4] * m[2] * m[13] - m[12] * m[1] * m[6] + m[12] * m[2] * m[5];
+  inv[3] = -m[1] * m[6] * m[11] + m[1] * m[7] * m[10] + m[5] * m[2] * m[11] - m[5] * m[3] * m[10] - m[9] * m[2] * m[7] + m[9] * m[3] * m[6];
+  inv[7] = m[0] * m[6] * m[11] - m[0] * m[7] * m[10] - m[4] * m[2] * m[11] + m[4] * m[3] * m[10] + m[8] * m[2] * m[7] - m[8] * m[3] * m[6];
+  inv[11] = -m[0] * m[5] * m[11] + m[0] * m[7] * m[9] + m[4] * m[1] * m[11] - m[4] * m[3] * m[9] - m[8] * m[1] * m[7] + m[8] * m[3] * m[5];
+  inv[15] = m[0] * m[5] * m[10] - m[0] * m[6] * m[9] - m[4] * m[1] * m[10] + m[4] * m[2] * m[9] + m[8] * m[1] * m[6] - m[8] * m[2] * m[5];
+  float det = m[0] * inv[0] + m[1] * inv[4] + m[2] * inv[8] + m[3] * inv[12];
+  if (det == 0.0f || det != det) return false;
+  float id = 1.0f / det;
+  for (int i = 0; i < 16; ++i) out[i] = inv[i] * id;
+  return true;
+}
+
+// ------------------------------------------------------------------ scene -> flat arrays
+int lower_scene(const std::vector<HostTexture>& textures, const std::vector<rt_material_desc>& materials,
+                std::vector<HostMesh>& meshes, const std::vector<HostObject>& objects, Lowered& L,
+                std::string& err) {
+  L = Lowered();
+  // BLASes, concatenated; child and triangle indices rebased to the global arrays
+  std::vector<uint32_t> node_base(meshes.size()), tri_base(meshes.size()), shade_base(meshes.size());
+  for (size_t mi = 0; mi < meshes.size(); ++mi) {
+    HostMesh& m = meshes[mi];
+    node_base[mi] = (uint32_t)(L.nodes.size() / RT_NODE_QUADS);
+    tri_base[mi] = (uint32_t)(L.tris.size() / RT_TRI_QUADS);
+    shade_base[mi] = (uint32_t)(L.shade.size() / RT_SHADE_QUADS);
+    size_t n0 = L.nodes.size();
+    L.nodes.insert(L.nodes.end(), m.nodes.begin(), m.nodes.end());
+    for (size_t q = n0; q < L.nodes.size(); q += 2) {
+      uint32_t count = L.nodes[q + 1].u[3];
+      L.nodes[q].u[3] += count ? tri_base[mi] : node_base[mi];
+    }
+    L.tris.insert(L.tris.end(), m.tris.begin(), m.tris.end());
+    L.shade.insert(L.shade.end(), m.shade.begin(), m.shade.end());
+    if ((L.tris.size() / RT_TRI_QUADS) >= (1u << 27)) {
+      err = "too many triangles";
+      return RT_ERR_UNSUPPORTED;
+    }
+  }
+
+  // materials: (albedo.xyz, roughness | ior) (emission.xyz, metallic)
+  L.mats.assign(materials.size() * RT_MAT_QUADS, Quad{});
+  for (size_t i = 0; i < materials.size(); ++i) {
+    const rt_material_desc& d = materials[i];
+    Quad* q = &L.mats[i * RT_MAT_QUADS];
+    for (int k = 0; k < 3; ++k) {
+      q[0].f[k] = d.albedo[k];
+      q[1].f[k] = d.tag == RT_MAT_DIELECTRIC ? 0.0f : d.emission[k];
+    }
+    q[0].f[3] = d.tag == RT_MAT_DIELECTRIC ? d.ior : d.roughness;
+    q[1].f[3] = d.metallic;
+  }
+
+  // textures
+  L.textures.assign(textures.size(), Quad{});
+  for (size_t i = 0; i < textures.size(); ++i) {
+    L.textures[i].u[0] = (uint32_t)L.texels.size();
+    L.textures[i].u[1] = textures[i].w;
+    L.textures[i].u[2] = textures[i].h;
+    L.texels.insert(L.texels.end(), textures[i].rgba.begin(), textures[i].rgba.end());
+  }
+  if (L.texels.empty()) L.texels.push_back(0);
+
+  // objects + TLAS primitives
+  L.objects.assign(objects.size() * RT_OBJ_QUADS, Quad{});
+  std::vector<BPrim> tprims;
+  int nvol = 0;
+  for (size_t oi = 0; oi < objects.size(); ++oi) {
+    const HostObject& o = objects[oi];
+    Quad* q = &L.objects[oi * RT_OBJ_QUADS];
+    q[0].i[0] = o.kind;
+    q[0].i[1] = o.material;
+    if (o.material >= (int)materials.size()) {
+      err = "object references a material id that does not exist";
+      return RT_ERR_INVALID;
+    }
+    q[0].i[2] = o.material >= 0 ? (int)materials[o.material].tag : RT_CLASS_PARAM_TEX;
+    q[0].i[3] = 0;
+    BPrim p;
+    bool bounded = true;
+    switch (o.kind) {
+      case RT_OBJ_MESH: {
+        if (o.mesh < 0 || o.mesh >= (int)meshes.size()) {
+          err = "instance references a mesh id that does not exist";
+          return RT_ERR_INVALID;
+        }
+        for (int k = 0; k < 5; ++k)
+          if (o.tex[k] >= (int)textures.size()) {
+            err = "instance references a texture id that does not exist";
+            return RT_ERR_INVALID;
+          }
+        const HostMesh& m = meshes[o.mesh];
+        for (int r = 0; r < 3; ++r)
+          for (int c = 0; c < 4; ++c) {
+            q[1 + r].f[c] = o.inv_xform[c * 4 + r];
+            q[4 + r].f[c] = o.xform[c * 4 + r];
+          }
+        uint32_t re = m.root_entry_local;
+        if (re != RT_ENTRY_NONE) {
+          if (re & RT_LEAF_FLAG) {
+            uint32_t first = (re & ~RT_LEAF_FLAG) >> 4, cnt = re & 15u;
+            re = pack_entry(first + tri_base[o.mesh], cnt);
+          } else {
+            re += node_base[o.mesh];
+          }
+        }
+        q[7].u[0] = re;
+        q[7].u[1] = shade_base[o.mesh];
+        q[7].i[2] = o.tex[0];
+        q[7].i[3] = o.tex[1];
+        q[8].i[0] = o.tex[2];
+        q[8].i[1] = o.tex[3];
+        q[8].i[2] = o.tex[4];
+        q[8].i[3] = 0;
+        if (m.n_reachable == 0) {
+          bounded = false;  // nothing to hit: not in the TLAS, not in the plane list either
+          break;
+        }
+        // world box = box of the 8 transformed corners of the (padded) object-space root box
+        for (int k = 0; k < 3; ++k) {
+          p.mn[k] = FLT_MAX;
+          p.mx[k] = -FLT_MAX;
+        }
+        for (int corner = 0; corner < 8; ++corner) {
+          float v[3] = {(corner & 1) ? m.root_max[0] : m.root_min[0], (corner & 2) ? m.root_max[1] : m.root_min[1],
+                        (corner & 4) ? m.root_max[2] : m.root_min[2]};
+          for (int k = 0; k < 3; ++k) {
+            float w = o.xform[k] * v[0] + o.xform[4 + k] * v[1] + o.xform[8 + k] * v[2] + o.xform[12 + k];
+            p.mn[k] = std::min(p.mn[k], w);
+            p.mx[k] = std::max(p.mx[k], w);
+          }
+        }
+        break;
+      }
+      case RT_OBJ_SPHERE:
+      case RT_OBJ_VOLUME: {
+        q[1].f[0] = o.a[0]; q[1].f[1] = o.a[1]; q[1].f[2] = o.a[2]; q[1].f[3] = o.radius;
+        if (o.kind == RT_OBJ_VOLUME) {
+          q[2].f[0] = o.density;
+          q[2].i[1] = nvol++;
+        }
+        float r = std::fabs(o.radius);
+        for (int k = 0; k < 3; ++k) {
+          p.mn[k] = o.a[k] - r;
+          p.mx[k] = o.a[k] + r;
+        }
+        break;
+      }
+      case RT_OBJ_TRIANGLE: {
+        float e1[3], e2[3];
+        for (int k = 0; k < 3; ++k) {
+          e1[k] = o.b[k] - o.a[k];
+          e2[k] = o.c[k] - o.a[k];
+        }
+        // normalize(e1 x e2), geometry.rs:449
+        float cx = e1[1] * e2[2] - e1[2] * e2[1], cy = e1[2] * e2[0] - e1[0] * e2[2], cz = e1[0] * e2[1] - e1[1] * e2[0];
+        float inv = 1.0f / std::sqrt(cx * cx + cy * cy + cz * cz);
+        q[1].f[0] = o.a[0]; q[1].f[1] = o.a[1]; q[1].f[2] = o.a[2]; q[1].f[3] = e1[0];
+        q[2].f[0] = e1[1]; q[2].f[1] = e1[2]; q[2].f[2] = e2[0]; q[2].f[3] = e2[1];
+        q[3].f[0] = e2[2]; q[3].f[1] = cx * inv; q[3].f[2] = cy * inv; q[3].f[3] = cz * inv;
+        for (int k = 0; k < 3; ++k) {
+          p.mn[k] = fmin3(o.a[k], o.b[k], o.c[k]);
+          p.mx[k] = fmax3(o.a[k], o.b[k], o.c[k]);
+        }
+        break;
+      }
+      case RT_OBJ_PLANE: {
+        q[1].f[0] = o.a[0]; q[1].f[1] = o.a[1]; q[1].f[2] = o.a[2];
+        q[2].f[0] = o.b[0]; q[2].f[1] = o.b[1]; q[2].f[2] = o.b[2];
+        bounded = false;
+        L.planes.push_back((int32_t)oi);
+        break;
+      }
+      default:
+        err = "unknown object kind";
+        return RT_ERR_INVALID;
+    }
+    if (bounded) {
+      bool finite = true;
+      for (int k = 0; k < 3; ++k) finite = finite && std::isfinite(p.mn[k]) && std::isfinite(p.mx[k]);
+      if (!finite) {
+        // cannot be bounded (e.g. NaN transform): test it for every ray instead
+        if (o.kind != RT_OBJ_MESH) L.planes.push_back((int32_t)oi);
+        continue;
+      }
+      float amax = 0.0f;
+      for (int k = 0; k < 3; ++k) amax = std::max(amax, std::max(std::fabs(p.mn[k]), std::fabs(p.mx[k])));
+      float pad = 1e-5f * amax + 1e-30f;
+      for (int k = 0; k < 3; ++k) {
+        p.mn[k] -= pad;
+        p.mx[k] += pad;
+        p.c[k] = 0.5f * (p.mn[k] + p.mx[k]);
+      }
+      p.id = (uint32_t)oi;
+      tprims.push_back(p);
+    }
+  }
+  L.n_volumes = (uint32_t)nvol;
+  if (L.planes.empty()) L.planes.push_back(-1);  // keep the buffer non-empty; n_planes stays 0
+  if (objects.empty()) L.objects.push_back(Quad{});
+  if (L.mats.empty()) L.mats.assign(RT_MAT_QUADS, Quad{});
+  if (L.textures.empty()) L.textures.push_back(Quad{});
+  if (L.tris.empty()) L.tris.assign(RT_TRI_QUADS, Quad{});
+  if (L.shade.empty()) L.shade.assign(RT_SHADE_QUADS, Quad{});
+
+  // TLAS: one object per leaf
+  if (!tprims.empty()) {
+    std::vector<BNode> tn;
+    build_bvh(tprims, 1, tn);
+    for (auto& n : tn)
+      if (n.count) n.leftFirst = tprims[n.leftFirst].id;  // leaf -> object index
+    uint32_t base = (uint32_t)(L.nodes.size() / RT_NODE_QUADS);
+    std::vector<Quad> tq;
+    nodes_to_quads(tn, 0.0f, tq);
+    for (size_t q = 0; q < tq.size(); q += 2)
+      if (tq[q + 1].u[3] == 0) tq[q].u[3] += base;
+    L.nodes.insert(L.nodes.end(), tq.begin(), tq.end());
+    L.tlas_root = tn[0].count ? pack_entry(tn[0].leftFirst, tn[0].count) : (tn[0].leftFirst + base);
+    for (int k = 0; k < 3; ++k) {
+      L.tlas_min[k] = tn[0].mn[k];
+      L.tlas_max[k] = tn[0].mx[k];
+    }
+  }
+  if (L.nodes.empty()) L.nodes.assign(RT_NODE_QUADS * 2, Quad{});
+  return RT_OK;
+}
+
+// ------------------------------------------------------------------ OBJ (tobj 3.2.0 semantics)
+// load_obj with single_index + triangulate (geometry.rs:140-148): faces are fan-triangulated
+// (0,i,i+1); vertices are de-duplicated on the (v,vt,vn) triple in first-seen order; a new
+// `o`/`g` statement after faces have been seen starts a new model and only the first model is
+// used (geometry.rs:157).
+namespace {
+struct Cursor {
+  const char* p;
+  const char* end;
+};
+inline void skip_ws(Cursor& c) {
+  while (c.p < c.end && (*c.p == ' ' || *c.p == '\t' || *c.p == '\r')) ++c.p;
+}
+inline bool parse_float(Cursor& c, float& out) {
+  skip_ws(c);
+  if (c.p >= c.end || *c.p == '\n') return false;
+  char buf[64];
+  size_t n = 0;
+  while (c.p < c.end && n < 63 && *c.p != ' ' && *c.p != '\t' && *c.p != '\r' && *c.p != '\n') buf[n++] = *c.p++;
+  buf[n] = 0;
+  char* e = nullptr;
+  out = std::strtof(buf, &e);
+  return e != buf;
+}
+inline bool parse_int(Cursor& c, long& out) {
+  if (c.p >= c.end) return false;
+  char* e = nullptr;
+  char buf[32];
+  size_t n = 0;
+  const char* q = c.p;
+  while (q < c.end && n < 31 && (*q == '-' || *q == '+' || (*q >= '0' && *q <= '9'))) buf[n++] = *q++;
+  buf[n] = 0;
+  if (n == 0) return false;
+  out = std::strtol(buf, &e, 10);
+  if (e == buf) return false;
+  c.p = q;
+  return true;
+}
+struct VKey {
+  long v, vt, vn;
+  bool operator==(const VKey& o) const { return v == o.v && vt == o.vt && vn == o.vn; }
+};
+struct VKeyHash {
+  size_t operator()(const VKey& k) const {
+    uint64_t h = (uint64_t)k.v * 0x9E3779B97F4A7C15ull;
+    h ^= (uint64_t)k.vt * 0xC2B2AE3D27D4EB4Full + (h << 6) + (h >> 2);
+    h ^= (uint64_t)k.vn * 0x165667B19E3779F9ull + (h << 6) + (h >> 2);
+    return (size_t)h;
+  }
+};
+}  // namespace
+
+int obj_parse(const char* text, size_t len, rt_obj_mesh* out, std::string& err) {
+  std::vector<float> P, T, N;           // file-order v / vt / vn
+  std::vector<float> pos, uv, nrm;      // de-duplicated outputs
+  std::vector<uint32_t> idx;
+  std::unordered_map<VKey, uint32_t, VKeyHash> map;
+  bool any_vt = false, any_vn = false, missing_vt = false, missing_vn = false;
+  bool have_faces = false;
+  Cursor c{text, text + len};
+  std::vector<VKey> face;
+  auto add_vertex = [&](const VKey& k) {
+    auto it = map.find(k);
+    if (it != map.end()) {
+      idx.push_back(it->second);
+      return;
+    }
+    uint32_t id = (uint32_t)map.size();
+    map.emplace(k, id);
+    pos.push_back(P[3 * k.v]); pos.push_back(P[3 * k.v + 1]); pos.push_back(P[3 * k.v + 2]);
+    if (k.vt >= 0) { uv.push_back(T[2 * k.vt]); uv.push_back(T[2 * k.vt + 1]); any_vt = true; }
+    else { uv.push_back(0.0f); uv.push_back(0.0f); missing_vt = true; }
+    if (k.vn >= 0) { nrm.push_back(N[3 * k.vn]); nrm.push_back(N[3 * k.vn + 1]); nrm.push_back(N[3 * k.vn + 2]); any_vn = true; }
+    else { nrm.push_back(0.0f); nrm.push_back(0.0f); nrm.push_back(0.0f); missing_vn = true; }
+    idx.push_back(id);
+  };
+  bool stop = false;
+  while (c.p < c.end && !stop) {
+    skip_ws(c);
+    const char* line = c.p;
+    const char* eol = line;
+    while (eol < c.end && *eol != '\n') ++eol;
+    Cursor l{line, eol};
+    size_t n = (size_t)(eol - line);
+    if (n >= 2 && line[0] == 'v' && (line[1] == ' ' || line[1] == '\t')) {
+      l.p += 2;
+      float x, y, z;
+      if (!parse_float(l, x) || !parse_float(l, y) || !parse_float(l, z)) { err = "bad v line"; return RT_ERR_IO; }
+      P.push_back(x); P.push_back(y); P.push_back(z);
+    } else if (n >= 3 && line[0] == 'v' && line[1] == 't' && (line[2] == ' ' || line[2] == '\t')) {
+      l.p += 3;
+      float u, v;
+      if (!parse_float(l, u) || !parse_float(l, v)) { err = "bad vt line"; return RT_ERR_IO; }
+      T.push_back(u); T.push_back(v);
+    } else if (n >= 3 && line[0] == 'v' && line[1] == 'n' && (line[2] == ' ' || line[2] == '\t')) {
+      l.p += 3;
+      float x, y, z;
+      if (!parse_float(l, x) || !parse_float(l, y) || !parse_float(l, z)) { err = "bad vn line"; return RT_ERR_IO; }
+      N.push_back(x); N.push_back(y); N.push_back(z);
+    } else if (n >= 2 && line[0] == 'f' && (line[1] == ' ' || line[1] == '\t')) {
+      l.p += 2;
+      face.clear();
+      for (;;) {
+        skip_ws(l);
+        if (l.p >= l.end) break;
+        VKey k{-1, -1, -1};
+        long v;
+        if (!parse_int(l, v)) { err = "bad f line"; return RT_ERR_IO; }
+        k.v = v < 0 ? (long)(P.size() / 3) + v : v - 1;
+        if (l.p < l.end && *l.p == '/') {
+          ++l.p;
+          long t;
+          if (parse_int(l, t)) k.vt = t < 0 ? (long)(T.size() / 2) + t : t - 1;
+          if (l.p < l.end && *l.p == '/') {
+            ++l.p;
+            long nn;
+            if (parse_int(l, nn)) k.vn = nn < 0 ? (long)(N.size() / 3) + nn : nn - 1;
+          }
+        }
+        if (k.v < 0 || k.v >= (long)(P.size() / 3) || k.vt >= (long)(T.size() / 2) || k.vn >= (long)(N.size() / 3)) {
+          err = "face index out of range";
+          return RT_ERR_IO;
+        }
+        face.push_back(k);
+      }
+      if (face.empty()) { err = "empty face"; return RT_ERR_IO; }
+      have_faces = true;
+      if (face.size() == 1) {  // point -> degenerate triangle (ignore_points: false)
+        add_vertex(face[0]); add_vertex(face[0]); add_vertex(face[0]);
+      } else if (face.size() == 2) {  // line -> degenerate triangle (ignore_lines: false)
+        add_vertex(face[0]); add_vertex(face[1]); add_vertex(face[1]);
+      } else {
+        for (size_t i = 1; i + 1 < face.size(); ++i) {
+          add_vertex(face[0]); add_vertex(face[i]); add_vertex(face[i + 1]);
+        }
+      }
+    } else if (n >= 2 && (line[0] == 'o' || line[0] == 'g') && (line[1] == ' ' || line[1] == '\t')) {
+      if (have_faces) stop = true;  // second model starts: the reference only uses models[0]
+    } else if (n == 1 && (line[0] == 'o' || line[0] == 'g')) {
+      if (have_faces) stop = true;
+    }
+    c.p = eol < c.end ? eol + 1 : eol;
+  }
+  if (!have_faces) { err = "OBJ has no faces"; return RT_ERR_IO; }
+  std::memset(out, 0, sizeof *out);
+  out->nverts = (uint32_t)(pos.size() / 3);
+  out->ntris = (uint32_t)(idx.size() / 3);
+  out->has_normals = any_vn && !missing_vn;
+  out->has_texcoords = any_vt && !missing_vt;
+  out->pos = (float*)std::malloc(pos.size() * 4 + 4);
+  out->nrm = (float*)std::malloc(nrm.size() * 4 + 4);
+  out->uv = (float*)std::malloc(uv.size() * 4 + 4);
+  out->idx = (uint32_t*)std::malloc(idx.size() * 4 + 4);
+  if (!out->pos || !out->nrm || !out->uv || !out->idx) { err = "out of memory"; return RT_ERR_IO; }
+  std::memcpy(out->pos, pos.data(), pos.size() * 4);
+  std::memcpy(out->nrm, nrm.data(), nrm.size() * 4);
+  std::memcpy(out->uv, uv.data(), uv.size() * 4);
+  std::memcpy(out->idx, idx.data(), idx.size() * 4);
+  return RT_OK;
+}
+
+// ------------------------------------------------------------------ TGA
+int tga_decode(const uint8_t* b, size_t len, uint8_t** rgb, uint32_t* w, uint32_t* h, std::string& err) {
+  if (len < 18) { err = "TGA too short"; return RT_ERR_IO; }
+  uint32_t idlen = b[0], cmaptype = b[1], type = b[2];
+  uint32_t cm_first = b[3] | (b[4] << 8), cm_len = b[5] | (b[6] << 8), cm_bpp = b[7];
+  uint32_t W = b[12] | (b[13] << 8), H = b[14] | (b[15] << 8), bpp = b[16], desc = b[17];
+  bool rle = type == 9 || type == 10 || type == 11;
+  uint32_t base = rle ? type - 8 : type;
+  if (!(base == 1 || base == 2 || base == 3) || W == 0 || H == 0) { err = "unsupported TGA type"; return RT_ERR_IO; }
+  if (base == 1 && (cmaptype != 1 || bpp != 8 || !(cm_bpp == 24 || cm_bpp == 32))) { err = "unsupported TGA palette"; return RT_ERR_IO; }
+  if (base == 2 && !(bpp == 24 || bpp == 32)) { err = "unsupported TGA depth"; return RT_ERR_IO; }
+  if (base == 3 && bpp != 8) { err = "unsupported TGA depth"; return RT_ERR_IO; }
+  size_t off = 18 + idlen;
+  const uint8_t* cmap = nullptr;
+  if (cmaptype == 1) {
+    cmap = b + off;
+    off += (size_t)cm_len * (cm_bpp / 8);
+  }
+  if (off > len) { err = "TGA truncated"; return RT_ERR_IO; }
+  uint32_t bytespp = bpp / 8;
+  size_t npix = (size_t)W * H;
+  std::vector<uint8_t> raw(npix * bytespp);
+  if (!rle) {
+    if (off + raw.size() > len) { err = "TGA truncated"; return RT_ERR_IO; }
+    std::memcpy(raw.data(), b + off, raw.size());
+  } else {
+    size_t o = 0, p = off;
+    while (o < raw.size()) {
+      if (p >= len) { err = "TGA truncated"; return RT_ERR_IO; }
+      uint8_t hd = b[p++];
+      uint32_t cnt = (hd & 0x7F) + 1;
+      if (hd & 0x80) {
+        if (p + bytespp > len) { err = "TGA truncated"; return RT_ERR_IO; }
+        for (uint32_t i = 0; i < cnt && o < raw.size(); ++i, o += bytespp) std::memcpy(&raw[o], b + p, bytespp);
+        p += bytespp;
+      } else {
+        size_t nb = (size_t)cnt * bytespp;
+        if (p + nb > len) { err = "TGA truncated"; return RT_ERR_IO; }
+        nb = std::min(nb, raw.size() - o);
+        std::memcpy(&raw[o], b + p, nb);
+        o += nb;
+        p += (size_t)cnt * bytespp;
+      }
+    }
+  }
+  uint8_t* out = (uint8_t*)std::malloc(npix * 3);
+  if (!out) { err = "out of memory"; return RT_ERR_IO; }
+  bool top = (desc & 0x20) != 0, right = (desc & 0x10) != 0;
+  for (uint32_t y = 0; y < H; ++y)
+    for (uint32_t x = 0; x < W; ++x) {
+      uint32_t sy = top ? y : H - 1 - y, sx = right ? W - 1 - x : x;
+      const uint8_t* s = &raw[((size_t)sy * W + sx) * bytespp];
+      uint8_t* d = &out[((size_t)y * W + x) * 3];
+      if (base == 2) {
+        d[0] = s[2]; d[1] = s[1]; d[2] = s[0];
+      } else if (base == 3) {
+        d[0] = d[1] = d[2] = s[0];
+      } else {
+        uint32_t ci = s[0];
+        if (ci < cm_first || ci - cm_first >= cm_len) { d[0] = d[1] = d[2] = 0; continue; }
+        const uint8_t* e = cmap + (size_t)(ci - cm_first) * (cm_bpp / 8);
+        d[0] = e[2]; d[1] = e[1]; d[2] = e[0];
+      }
+    }
+  *rgb = out;
+  *w = W;
+  *h = H;
+  return RT_OK;
+}
+
+int tga_encode_rgb8(const uint8_t* rgb, uint32_t w, uint32_t h, uint8_t** bytes, size_t* len) {
+  if (!rgb || !w || !h || w > 65535 || h > 65535) return RT_ERR_INVALID;
+  size_t n = 18 + (size_t)w * h * 3;
+  uint8_t* o = (uint8_t*)std::malloc(n);
+  if (!o) return RT_ERR_IO;
+  std::memset(o, 0, 18);
+  o[2] = 2;
+  o[12] = w & 255; o[13] = w >> 8; o[14] = h & 255; o[15] = h >> 8;
+  o[16] = 24;
+  o[17] = 0x20;  // top-left origin
+  for (size_t i = 0; i < (size_t)w * h; ++i) {
+    o[18 + 3 * i] = rgb[3 * i + 2];
+    o[18 + 3 * i + 1] = rgb[3 * i + 1];
+    o[18 + 3 * i + 2] = rgb[3 * i];
+  }
+  *bytes = o;
+  *len = n;
+  return RT_OK;
+}
+
+}  // namespace rt

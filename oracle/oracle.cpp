@@ -1,0 +1,1042 @@
+// oracle.cpp — TEST INFRASTRUCTURE, NOT PRODUCT CODE.
+//
+// CPU restatement of the hot path of mbk6/CS397RayTracingSP22 (Rust), function by
+// function, with every behavioural quirk kept.  Only tests/,
+// __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may
+// build, load or call this file.  The product library (librt_b200.so) never does.
+//
+// PARITY UNPINNED UPSTREAM: the reference ships no tests, golden vectors or
+// known-answer values, cannot be compiled here (no cargo/rustc, crates not
+// vendored) and draws every random number from OS-seeded rand::thread_rng(), so
+// two runs of the reference never agree sample for sample.  This file is pinned
+// instead by (i) analytic known-answer tests derived from the reference's formulas
+// (tests/test_oracle_kat.py) and (ii) its two independent closest-hit modes
+// agreeing with each other (reference tree replay vs brute force).
+//
+// What is NOT the reference: the random number source.  rand::thread_rng()
+// (tracing.rs:72,83,164; geometry.rs:517; materials.rs:84,120) is replaced by
+// Philox4x32-10 keyed on (pixel, sample, bounce, block), and the rejection loops of
+// rand_sphere_vec / rand_disk_vec (tracing.rs:71-89) by direct, distribution-
+// identical ball / disk maps.  DESIGN.md "RNG contract" states the mapping; the
+// CUDA kernels implement the same contract independently.
+//
+// Arithmetic: compiled with -ffp-contract=off and no fast-math so every f32
+// operation is a single IEEE operation, as in Rust.  Third-party crate behaviour
+// restated here (sources not under /root/reference): cgmath 0.18.0 (dot/cross/
+// normalize/Matrix ops/Quaternion::from_arc), rand 0.8.4 (replaced), image 0.23.14
+// (get_pixel().to_rgb() on decoded RGB8).
+//
+// Build: see oracle/Makefile.
+
+#include <algorithm>
+#include <cfloat>
+#include <cmath>
+#include <cstdint>
+#include <cstdlib>
+#include <cstring>
+#include <memory>
+#include <vector>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+#include "../include/rt_b200.h"
+
+namespace {
+
+// ---------------------------------------------------------------- vectors (cgmath)
+struct V3 {
+  float x, y, z;
+};
+inline V3 v3(float x, float y, float z) { return V3{x, y, z}; }
+inline V3 operator+(V3 a, V3 b) { return {a.x + b.x, a.y + b.y, a.z + b.z}; }
+inline V3 operator-(V3 a, V3 b) { return {a.x - b.x, a.y - b.y, a.z - b.z}; }
+inline V3 operator-(V3 a) { return {-a.x, -a.y, -a.z}; }
+inline V3 operator*(V3 a, float s) { return {a.x * s, a.y * s, a.z * s}; }
+inline V3 operator*(float s, V3 a) { return {a.x * s, a.y * s, a.z * s}; }
+inline V3 operator/(V3 a, float s) { return {a.x / s, a.y / s, a.z / s}; }
+inline V3 mul_elem(V3 a, V3 b) { return {a.x * b.x, a.y * b.y, a.z * b.z}; }
+// cgmath: mul_element_wise(...).sum() => (x + y) + z
+inline float dot(V3 a, V3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+inline float mag2(V3 a) { return dot(a, a); }
+inline V3 cross(V3 a, V3 b) {
+  return {a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x};
+}
+// cgmath InnerSpace::normalize => self * (1 / magnitude)
+inline V3 normalize(V3 a) { return a * (1.0f / std::sqrt(mag2(a))); }
+inline float comp(V3 a, int i) { return i == 0 ? a.x : (i == 1 ? a.y : a.z); }
+
+// f32::max / f32::min ignore a NaN operand
+inline float rmax(float a, float b) { return std::fmax(a, b); }
+inline float rmin(float a, float b) { return std::fmin(a, b); }
+// f32::clamp
+inline float rclamp(float v, float lo, float hi) {
+  if (v < lo) return lo;
+  if (v > hi) return hi;
+  return v;
+}
+
+// column-major 4x4 (cgmath Matrix4)
+struct M4 {
+  float m[16];
+};
+// (self * v.extend(0)).truncate()
+inline V3 transform_vector(const M4& a, V3 v) {
+  const float* m = a.m;
+  return {m[0] * v.x + m[4] * v.y + m[8] * v.z + m[12] * 0.0f,
+          m[1] * v.x + m[5] * v.y + m[9] * v.z + m[13] * 0.0f,
+          m[2] * v.x + m[6] * v.y + m[10] * v.z + m[14] * 0.0f};
+}
+// Point3::from_homogeneous(self * p.to_homogeneous())
+inline V3 transform_point(const M4& a, V3 p) {
+  const float* m = a.m;
+  float x = m[0] * p.x + m[4] * p.y + m[8] * p.z + m[12] * 1.0f;
+  float y = m[1] * p.x + m[5] * p.y + m[9] * p.z + m[13] * 1.0f;
+  float z = m[2] * p.x + m[6] * p.y + m[10] * p.z + m[14] * 1.0f;
+  float w = m[3] * p.x + m[7] * p.y + m[11] * p.z + m[15] * 1.0f;
+  float iw = 1.0f / w;
+  return {x * iw, y * iw, z * iw};
+}
+inline M4 transpose(const M4& a) {
+  M4 r;
+  for (int c = 0; c < 4; ++c)
+    for (int q = 0; q < 4; ++q) r.m[c * 4 + q] = a.m[q * 4 + c];
+  return r;
+}
+
+// ---------------------------------------------------------------- RNG contract
+struct U4 {
+  uint32_t v[4];
+};
+inline U4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0,
+                        uint32_t k1) {
+  const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+  for (int r = 0; r < 10; ++r) {
+    uint64_t p0 = (uint64_t)M0 * c0, p1 = (uint64_t)M1 * c2;
+    uint32_t hi0 = (uint32_t)(p0 >> 32), lo0 = (uint32_t)p0;
+    uint32_t hi1 = (uint32_t)(p1 >> 32), lo1 = (uint32_t)p1;
+    uint32_t n0 = hi1 ^ c1 ^ k0, n1 = lo1, n2 = hi0 ^ c3 ^ k1, n3 = lo0;
+    c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+    k0 += W0; k1 += W1;
+  }
+  return U4{{c0, c1, c2, c3}};
+}
+inline float u01(uint32_t x) { return (float)(x >> 8) * (1.0f / 16777216.0f); }
+const uint32_t BOUNCE_CAMERA = 0xFFFFFFFFu;
+const float PI_F = 3.14159265358979323846f;  // std::f32::consts::PI
+
+struct RngKey {
+  uint32_t k0, k1, pixel, sample;
+};
+inline U4 draw(const RngKey& k, uint32_t bounce, uint32_t block) {
+  return philox4x32_10(k.pixel, k.sample, bounce, block, k.k0, k.k1);
+}
+// stands in for rand_sphere_vec (tracing.rs:71-79): uniform in the unit ball, NOT normalised
+inline V3 ball_from(uint32_t a, uint32_t b, uint32_t c) {
+  float rad = std::cbrt(u01(a));
+  float zc = 1.0f - 2.0f * u01(b);
+  float s = std::sqrt(rmax(0.0f, 1.0f - zc * zc));
+  float phi = (2.0f * PI_F) * u01(c);
+  return {rad * s * std::cos(phi), rad * zc, rad * s * std::sin(phi)};
+}
+// stands in for rand_disk_vec (tracing.rs:81-89)
+inline V3 disk_from(uint32_t a, uint32_t b) {
+  float rr = std::sqrt(u01(a));
+  float phi = (2.0f * PI_F) * u01(b);
+  return {rr * std::cos(phi), rr * std::sin(phi), 0.0f};
+}
+
+// ---------------------------------------------------------------- scene
+struct Ray {
+  V3 origin, direction;
+};
+struct Material {
+  rt_material_desc d;
+};
+struct Texture {
+  uint32_t w, h;
+  std::vector<uint8_t> rgb;
+};
+// texture.rs:26-32
+inline V3 tex_sample(const Texture& t, float u, float v) {
+  float fx = rclamp(u, 0.0f, 0.999f) * (float)t.w;
+  float fy = (1.0f - rclamp(v, 0.0f, 0.999f)) * (float)t.h;
+  // Rust `as u32` saturates and maps NaN to 0
+  uint32_t x = (fx != fx || fx <= 0.0f) ? 0u : (fx >= 4294967295.0f ? 0xFFFFFFFFu : (uint32_t)fx);
+  uint32_t y = (fy != fy || fy <= 0.0f) ? 0u : (fy >= 4294967295.0f ? 0xFFFFFFFFu : (uint32_t)fy);
+  x = std::min(x, t.w - 1);
+  y = std::min(y, t.h - 1);
+  const uint8_t* p = &t.rgb[((size_t)y * t.w + x) * 3];
+  return {(float)p[0] / 255.0f, (float)p[1] / 255.0f, (float)p[2] / 255.0f};
+}
+
+struct Hit {
+  float distance;
+  V3 hitpoint;
+  V3 normal;
+  bool frontface;
+  bool has_uv;
+  float u, v;
+  V3 tangent, bitangent;
+  // "Arc<dyn Material>": an index, or a per-hit ParameterizedMaterial value
+  int material;       // index into materials, or -1 when `param` is used
+  rt_material_desc param;
+  int obj;   // top-level object index (bookkeeping for the parity hooks)
+  int prim;  // triangle index inside a mesh
+};
+// RayHit::new, tracing.rs:121-133
+inline Hit make_hit(float distance, V3 normal, int material, const Ray& ray) {
+  Hit h;
+  h.frontface = dot(normal, ray.direction) < 0.0f;
+  h.distance = distance;
+  h.hitpoint = ray.origin + ray.direction * distance;
+  h.normal = h.frontface ? normal : -normal;
+  h.material = material;
+  h.has_uv = false;
+  h.u = h.v = 0.0f;
+  h.tangent = h.bitangent = v3(0, 0, 0);
+  h.obj = -1;
+  h.prim = 0;
+  return h;
+}
+
+struct AABB {
+  V3 min, max;
+};
+// geometry.rs:52-68 — strict: rejects when tmax <= tmin
+inline bool aabb_hit(const AABB& b, const Ray& ray, float t_min, float t_max) {
+  float tmin = t_min, tmax = t_max;
+  for (int axis = 0; axis < 3; ++axis) {
+    float inv_d = 1.0f / comp(ray.direction, axis);
+    float t0 = (comp(b.min, axis) - comp(ray.origin, axis)) * inv_d;
+    float t1 = (comp(b.max, axis) - comp(ray.origin, axis)) * inv_d;
+    if (inv_d < 0.0f) std::swap(t0, t1);
+    tmin = rmax(t0, tmin);
+    tmax = rmin(t1, tmax);
+    if (tmax <= tmin) return false;
+  }
+  return true;
+}
+
+struct Mesh {
+  std::vector<float> pos, nrm, uv;
+  std::vector<uint32_t> idx;
+  uint32_t ntris() const { return (uint32_t)(idx.size() / 3); }
+  // index-order tree, geometry.rs:190-217: node over [start,end), mid = start+(end-start)/2,
+  // leaf = triangle `start` (the sort at :207 permutes `tris`, which the leaves never read)
+  struct Node {
+    AABB box;
+    int left, right;  // node ids, -1 for leaf
+    int tri;          // leaf triangle or -1
+  };
+  std::vector<Node> nodes;
+  int root = -1;
+
+  void tri_pos(uint32_t t, V3& a, V3& b, V3& c) const {  // geometry.rs:223-229
+    uint32_t i0 = idx[t * 3], i1 = idx[t * 3 + 1], i2 = idx[t * 3 + 2];
+    a = v3(pos[i0 * 3], pos[i0 * 3 + 1], pos[i0 * 3 + 2]);
+    b = v3(pos[i1 * 3], pos[i1 * 3 + 1], pos[i1 * 3 + 2]);
+    c = v3(pos[i2 * 3], pos[i2 * 3 + 1], pos[i2 * 3 + 2]);
+  }
+  void tri_nrm(uint32_t t, V3& a, V3& b, V3& c) const {  // geometry.rs:237-243
+    uint32_t i0 = idx[t * 3], i1 = idx[t * 3 + 1], i2 = idx[t * 3 + 2];
+    a = v3(nrm[i0 * 3], nrm[i0 * 3 + 1], nrm[i0 * 3 + 2]);
+    b = v3(nrm[i1 * 3], nrm[i1 * 3 + 1], nrm[i1 * 3 + 2]);
+    c = v3(nrm[i2 * 3], nrm[i2 * 3 + 1], nrm[i2 * 3 + 2]);
+  }
+  void tri_uv(uint32_t t, float* a, float* b, float* c) const {  // geometry.rs:230-236
+    uint32_t i0 = idx[t * 3], i1 = idx[t * 3 + 1], i2 = idx[t * 3 + 2];
+    a[0] = uv[i0 * 2]; a[1] = uv[i0 * 2 + 1];
+    b[0] = uv[i1 * 2]; b[1] = uv[i1 * 2 + 1];
+    c[0] = uv[i2 * 2]; c[1] = uv[i2 * 2 + 1];
+  }
+  AABB tri_box(uint32_t t) const {  // geometry.rs:367-381
+    V3 a, b, c;
+    tri_pos(t, a, b, c);
+    AABB r;
+    r.min = v3(rmin(a.x, rmin(b.x, c.x)), rmin(a.y, rmin(b.y, c.y)), rmin(a.z, rmin(b.z, c.z)));
+    r.max = v3(rmax(a.x, rmax(b.x, c.x)), rmax(a.y, rmax(b.y, c.y)), rmax(a.z, rmax(b.z, c.z)));
+    return r;
+  }
+  int build(uint32_t start, uint32_t end) {
+    Node n;
+    n.left = n.right = n.tri = -1;
+    if (end - start == 1) {
+      n.box = tri_box(start);
+      n.tri = (int)start;
+    } else {
+      uint32_t mid = start + (end - start) / 2;
+      int l = build(start, mid);
+      int r = build(mid, end);
+      const AABB &a = nodes[l].box, &b = nodes[r].box;  // geometry.rs:28-41
+      n.box.min = v3(rmin(a.min.x, b.min.x), rmin(a.min.y, b.min.y), rmin(a.min.z, b.min.z));
+      n.box.max = v3(rmax(a.max.x, b.max.x), rmax(a.max.y, b.max.y), rmax(a.max.z, b.max.z));
+      n.left = l;
+      n.right = r;
+    }
+    nodes.push_back(n);
+    return (int)nodes.size() - 1;
+  }
+  void build_bvh() {
+    nodes.clear();
+    nodes.reserve(2 * (size_t)ntris());
+    root = ntris() ? build(0, ntris()) : -1;
+  }
+};
+
+// geometry.rs:245-250
+inline V3 get_tangent(const float* uv1, const float* uv2, const float* uv3, V3 p1, V3 p2, V3 p3) {
+  float u1 = uv1[0], u2 = uv2[0], u3 = uv3[0];
+  float v1 = uv1[1], v2 = uv2[1], v3_ = uv3[1];
+  return ((v3_ - v1) * (p2 - p1) - (v2 - v1) * (p3 - p1)) / ((u2 - u1) * (v3_ - v1) - (v2 - v1) * (u3 - u1));
+}
+
+// IndexedTriangle::intersect_ray, geometry.rs:331-366
+inline bool indexed_triangle_hit(const Mesh& m, uint32_t t, const Ray& ray, float t_min, float t_max,
+                                 Hit& out) {
+  V3 a, b, c;
+  m.tri_pos(t, a, b, c);
+  const float EPSILON = 0.0001f;
+  V3 e1 = b - a, e2 = c - a;
+  V3 q = cross(ray.direction, e2);
+  float g = dot(e1, q);
+  if (std::fabs(g) < EPSILON) return false;
+  float f = 1.0f / g;
+  V3 s = ray.origin - a;
+  float u = f * dot(s, q);
+  if (u < 0.0f) return false;
+  V3 r = cross(s, e1);
+  float v = f * dot(ray.direction, r);
+  if (v < 0.0f || u + v > 1.0f) return false;
+  float tt = f * dot(e2, r);
+  if (tt < t_min || tt > t_max) return false;
+  V3 na, nb, nc;
+  m.tri_nrm(t, na, nb, nc);
+  V3 mesh_normal = normalize(u * nb + v * nc + (1.0f - u - v) * na);
+  Hit h = make_hit(tt, mesh_normal, /*Lambertian::default placeholder*/ -2, ray);
+  float ta[2], tb[2], tc[2];
+  m.tri_uv(t, ta, tb, tc);
+  float w = 1.0f - u - v;
+  h.has_uv = true;
+  h.u = u * tb[0] + v * tc[0] + w * ta[0];
+  h.v = u * tb[1] + v * tc[1] + w * ta[1];
+  V3 tan_approx = get_tangent(ta, tb, tc, a, b, c);
+  V3 bitangent = normalize(cross(h.normal, tan_approx));
+  V3 tangent = normalize(cross(bitangent, h.normal));
+  h.tangent = tangent;
+  h.bitangent = bitangent;
+  h.prim = (int)t;
+  out = h;
+  return true;
+}
+
+struct Counters {
+  uint64_t rays = 0, box_tests = 0, tri_tests = 0;
+};
+
+// BVHNode::intersect_ray, geometry.rs:94-119
+bool bvh_hit(const Mesh& m, int node, const Ray& ray, float t_min, float t_max, Hit& out,
+             Counters* cnt) {
+  const Mesh::Node& n = m.nodes[node];
+  if (n.tri >= 0) {
+    if (cnt) cnt->tri_tests++;
+    return indexed_triangle_hit(m, (uint32_t)n.tri, ray, t_min, t_max, out);
+  }
+  bool have = false;
+  float best_t = t_max;
+  if (cnt) cnt->box_tests++;
+  if (aabb_hit(n.box, ray, t_min, t_max)) {
+    Hit h;
+    if (n.left >= 0 && bvh_hit(m, n.left, ray, t_min, t_max, h, cnt)) {
+      out = h;
+      have = true;
+      best_t = h.distance;
+    }
+    if (n.right >= 0 && bvh_hit(m, n.right, ray, t_min, best_t, h, cnt)) {
+      out = h;
+      have = true;
+    }
+  }
+  return have;
+}
+
+enum ObjKind { OBJ_MESH = 0, OBJ_SPHERE = 1, OBJ_TRIANGLE = 2, OBJ_PLANE = 3, OBJ_VOLUME = 4 };
+struct Object {
+  int kind;
+  // mesh instance
+  int mesh = -1;
+  M4 transform, inv_transform;
+  int tex[5] = {-1, -1, -1, -1, -1};
+  // shared
+  int material = -1;
+  V3 a, b, c;   // sphere: a = center; triangle: a,b,c; plane: a = point, b = normal
+  float radius = 0.0f;
+  float density = 0.0f;
+  int vol_index = -1;  // ordinal among volumes (RNG contract)
+};
+
+}  // namespace
+
+struct orc_scene {
+  std::vector<Texture> textures;
+  std::vector<Material> materials;
+  std::vector<std::unique_ptr<Mesh>> meshes;
+  std::vector<std::vector<uint8_t>> reach;  // brute mode: reachability masks per mesh
+  std::vector<Object> objects;
+  int n_volumes = 0;
+};
+
+namespace {
+
+enum Mode { MODE_REF_TREE = 0, MODE_BRUTE = 1 };
+
+// Sphere::intersect_ray, geometry.rs:395-413
+inline bool sphere_hit(V3 center, float radius, int material, const Ray& ray, float t_min, float t_max,
+                       Hit& out) {
+  V3 f = ray.origin - center;
+  float a = mag2(ray.direction);
+  float b = 2.0f * dot(f, ray.direction);
+  float c = mag2(f) - radius * radius;
+  float d = b * b - 4.0f * a * c;
+  if (d < 0.0f) return false;
+  float t1 = (-b - std::sqrt(d)) / (2.0f * a);
+  float t2 = (-b + std::sqrt(d)) / (2.0f * a);
+  float t = t1 >= t_min ? t1 : t2;
+  V3 hitpoint = ray.origin + t * ray.direction;
+  if (t < t_min || t > t_max) return false;
+  out = make_hit(t, normalize(hitpoint - center), material, ray);
+  return true;
+}
+// Triangle::intersect_ray, geometry.rs:431-450
+inline bool triangle_hit(const Object& o, const Ray& ray, float t_min, float t_max, Hit& out) {
+  const float EPSILON = 0.0001f;
+  V3 e1 = o.b - o.a, e2 = o.c - o.a;
+  V3 q = cross(ray.direction, e2);
+  float a = dot(e1, q);
+  if (std::fabs(a) < EPSILON) return false;
+  float f = 1.0f / a;
+  V3 s = ray.origin - o.a;
+  float u = f * dot(s, q);
+  if (u < 0.0f) return false;
+  V3 r = cross(s, e1);
+  float v = f * dot(ray.direction, r);
+  if (v < 0.0f || u + v > 1.0f) return false;
+  float t = f * dot(e2, r);
+  if (t < t_min || t > t_max) return false;
+  out = make_hit(t, normalize(cross(e1, e2)), o.material, ray);
+  return true;
+}
+inline float signum(float x) {  // f32::signum
+  if (x != x) return x;
+  return std::signbit(x) ? -1.0f : 1.0f;
+}
+// Plane::intersect_ray, geometry.rs:474-489
+inline bool plane_hit(const Object& o, const Ray& ray, float t_min, float t_max, Hit& out) {
+  V3 to_ray_origin = ray.origin - o.a;
+  float origin_dist = dot(to_ray_origin, o.b);
+  V3 n = signum(origin_dist) * o.b;
+  float d = dot(ray.direction, n);
+  if (d >= 0.0f) return false;
+  float t = std::fabs(origin_dist) / std::fabs(d);
+  if (t < t_min || t > t_max) return false;
+  out = make_hit(t, n, o.material, ray);
+  return true;
+}
+// ConvexVolume::intersect_ray with a Sphere boundary, geometry.rs:502-526
+inline bool volume_hit(const Object& o, const Ray& ray, float t_min, float t_max, const RngKey& key,
+                       uint32_t bounce, Hit& out) {
+  Hit e;
+  if (!sphere_hit(o.a, o.radius, -1, ray, -FLT_MAX, FLT_MAX, e)) return false;  // f32::MIN = -MAX
+  float t_entr = e.distance;
+  if (!sphere_hit(o.a, o.radius, -1, ray, t_entr + 0.0001f, FLT_MAX, e)) return false;
+  float t_exit = e.distance;
+  if (t_exit < t_min || t_entr > t_max) return false;
+  float t_start = rmax(t_entr, t_min);
+  float t_end = rmin(t_exit, t_max);
+  float dist_in_volume = t_end - t_start;
+  U4 r = draw(key, bounce, 1u + (uint32_t)o.vol_index / 4u);
+  float U = u01(r.v[o.vol_index & 3]);
+  float dist_before_scatter = (-1.0f / o.density) * std::log(U);
+  if (dist_before_scatter < dist_in_volume) {
+    out = make_hit(t_start + dist_before_scatter, v3(0, 0, 0), o.material, ray);
+    return true;
+  }
+  return false;
+}
+
+// StaticMesh::get_adjusted_normal, geometry.rs:274-298
+inline V3 adjusted_normal(const orc_scene& sc, const Object& o, const Hit& hit) {
+  V3 n = hit.normal;
+  if (o.tex[4] >= 0 && hit.has_uv) {
+    V3 s = tex_sample(sc.textures[o.tex[4]], hit.u, hit.v);
+    V3 nm = 2.0f * s - v3(1.0f, 1.0f, 1.0f);
+    // Matrix3::from_cols(tangent, bitangent, normal) * nm
+    n = hit.tangent * nm.x + hit.bitangent * nm.y + hit.normal * nm.z;
+  }
+  return normalize(transform_vector(transpose(o.inv_transform), n));
+}
+// StaticMesh::get_material_at_uv, geometry.rs:253-271
+inline void material_at_uv(const orc_scene& sc, const Object& o, Hit& hit) {
+  if (o.material >= 0) {
+    hit.material = o.material;
+    return;
+  }
+  rt_material_desc p;
+  std::memset(&p, 0, sizeof p);
+  p.tag = RT_MAT_PARAMETERIZED;
+  V3 albedo = o.tex[0] >= 0 ? tex_sample(sc.textures[o.tex[0]], hit.u, hit.v) : v3(0, 0, 0);
+  V3 emission = o.tex[1] >= 0 ? tex_sample(sc.textures[o.tex[1]], hit.u, hit.v) : v3(0, 0, 0);
+  float metallic = o.tex[2] >= 0 ? tex_sample(sc.textures[o.tex[2]], hit.u, hit.v).x : 0.0f;
+  float roughness = o.tex[3] >= 0 ? tex_sample(sc.textures[o.tex[3]], hit.u, hit.v).x : 1.0f;
+  p.albedo[0] = albedo.x; p.albedo[1] = albedo.y; p.albedo[2] = albedo.z;
+  p.emission[0] = emission.x; p.emission[1] = emission.y; p.emission[2] = emission.z;
+  p.metallic = metallic;
+  p.roughness = roughness;
+  hit.material = -1;
+  hit.param = p;
+}
+
+// brute-force stand-in for the tree: every reachable triangle with the same [t_min,t_max];
+// keep the smallest t, and among equal t the highest index (what left-then-right with
+// t_max = best_t and inclusive bounds produces, geometry.rs:105-115,349)
+inline bool brute_mesh_hit(const Mesh& m, const std::vector<uint8_t>& reach, const Ray& ray, float t_min,
+                           float t_max, Hit& out, Counters* cnt) {
+  bool have = false;
+  float best = t_max;
+  for (uint32_t t = 0; t < m.ntris(); ++t) {
+    if (!reach[t]) continue;
+    Hit h;
+    if (cnt) cnt->tri_tests++;
+    if (indexed_triangle_hit(m, t, ray, t_min, best, h)) {
+      out = h;
+      best = h.distance;
+      have = true;
+    }
+  }
+  return have;
+}
+
+// StaticMesh::intersect_ray, geometry.rs:301-314
+inline bool mesh_hit(const orc_scene& sc, const Object& o, int obj_index, const Ray& ray, float t_min,
+                     float t_max, int mode, Hit& out, Counters* cnt) {
+  const Mesh& m = *sc.meshes[o.mesh];
+  if (m.root < 0) return false;
+  Ray tr;
+  tr.origin = transform_point(o.inv_transform, ray.origin);
+  tr.direction = transform_vector(o.inv_transform, ray.direction);
+  Hit h;
+  bool ok = mode == MODE_REF_TREE ? bvh_hit(m, m.root, tr, t_min, t_max, h, cnt)
+                                  : brute_mesh_hit(m, sc.reach[o.mesh], tr, t_min, t_max, h, cnt);
+  if (!ok) return false;
+  h.hitpoint = transform_point(o.transform, h.hitpoint);
+  h.normal = adjusted_normal(sc, o, h);
+  material_at_uv(sc, o, h);
+  h.obj = obj_index;
+  out = h;
+  return true;
+}
+
+// Scene::intersect_ray, tracing.rs:327-346
+bool scene_hit(const orc_scene& sc, const Ray& ray, float t_min, float t_max, int mode, const RngKey& key,
+               uint32_t bounce, Hit& best, Counters* cnt) {
+  bool have = false;
+  if (cnt) cnt->rays++;
+  for (size_t i = 0; i < sc.objects.size(); ++i) {
+    const Object& o = sc.objects[i];
+    Hit h;
+    bool ok = false;
+    switch (o.kind) {
+      case OBJ_MESH: ok = mesh_hit(sc, o, (int)i, ray, t_min, t_max, mode, h, cnt); break;
+      case OBJ_SPHERE: ok = sphere_hit(o.a, o.radius, o.material, ray, t_min, t_max, h); break;
+      case OBJ_TRIANGLE: ok = triangle_hit(o, ray, t_min, t_max, h); break;
+      case OBJ_PLANE: ok = plane_hit(o, ray, t_min, t_max, h); break;
+      case OBJ_VOLUME: ok = volume_hit(o, ray, t_min, t_max, key, bounce, h); break;
+    }
+    if (!ok) continue;
+    h.obj = (int)i;
+    if (!have || h.distance < best.distance) {
+      best = h;
+      have = true;
+    }
+  }
+  return have;
+}
+
+// ---------------------------------------------------------------- materials
+inline V3 reflect(V3 v, V3 n) { return v - 2.0f * dot(v, n) * n; }  // tracing.rs:54-56
+inline float powi5(float x) {  // llvm powi(.,5): x * (x^2)^2
+  float x2 = x * x;
+  return x * (x2 * x2);
+}
+inline float fresnel(V3 v, V3 n, float ir) {  // tracing.rs:58-62
+  float q = (ir - 1.0f) / (ir + 1.0f);
+  float r0 = q * q;
+  return r0 + (1.0f - r0) * powi5(1.0f - std::fabs(dot(v, n)));
+}
+inline V3 refract(V3 v, V3 n, float eta) {  // tracing.rs:64-69
+  float cos_theta = rmin(dot(-v, n), 1.0f);
+  V3 r_out_perp = eta * (v + cos_theta * n);
+  V3 r_out_parallel = -std::sqrt(std::fabs(1.0f - mag2(r_out_perp))) * n;
+  return r_out_perp + r_out_parallel;
+}
+inline V3 lerpvec(V3 a, V3 b, float k) { return (1.0f - k) * a + k * b; }  // tracing.rs:95-97
+
+// cgmath Quaternion::from_arc(unit_y, n, None) then rotate_vector is what
+// Basis3::between_vectors does (materials.rs:176-177).
+// approx::ulps_eq! with cgmath's defaults (epsilon = f32::EPSILON, max_ulps = 4)
+inline bool ulps_eq(float a, float b) {
+  if (std::fabs(a - b) <= FLT_EPSILON) return true;
+  if (std::signbit(a) != std::signbit(b)) return false;
+  int32_t ia, ib;
+  std::memcpy(&ia, &a, 4);
+  std::memcpy(&ib, &b, 4);
+  int64_t d = (int64_t)ia - (int64_t)ib;
+  return (d < 0 ? -d : d) <= 4;
+}
+inline V3 rotate_y_to(V3 n, V3 d) {
+  const V3 a = v3(0.0f, 1.0f, 0.0f);
+  float mag_avg = std::sqrt(mag2(a) * mag2(n));
+  float dt = dot(a, n);
+  float s;
+  V3 v;
+  if (ulps_eq(dt, mag_avg)) {  // same direction: Quaternion::one()
+    return d;
+  } else if (ulps_eq(dt, -mag_avg)) {
+    // opposite: from_axis_angle(normalize(unit_x × a) = +z, pi): s = cos(pi/2), v = z*sin(pi/2)
+    s = -4.371139e-8f;
+    v = v3(0.0f, 0.0f, 1.0f);
+  } else {
+    s = mag_avg + dt;
+    v = cross(a, n);
+    float inv = 1.0f / std::sqrt(s * s + mag2(v));  // Quaternion::normalize
+    s = s * inv;
+    v = v * inv;
+  }
+  // Quaternion * Vector3: tmp = v×d + d*s; (v×tmp)*2 + d
+  V3 tmp = cross(v, d) + d * s;
+  return cross(v, tmp) * 2.0f + d;
+}
+// sample_hemisphere, materials.rs:171-178
+inline V3 sample_hemisphere(V3 normal, V3 ball) {
+  V3 dir = ball;
+  dir.y = std::fabs(dir.y);
+  return rotate_y_to(normal, dir);
+}
+
+struct Scatter {
+  Ray ray;
+  V3 brdf;
+  float pdf;
+};
+// Material::scatter for the five materials, materials.rs:33-166
+inline Scatter scatter(const rt_material_desc& m, const Hit& hit, const Ray& ray, const U4& r) {
+  Scatter s;
+  s.ray.origin = hit.hitpoint;
+  V3 albedo = v3(m.albedo[0], m.albedo[1], m.albedo[2]);
+  float u_choice = u01(r.v[0]);
+  V3 ball = ball_from(r.v[1], r.v[2], r.v[3]);
+  switch (m.tag) {
+    case RT_MAT_LAMBERTIAN:
+      s.ray.direction = sample_hemisphere(hit.normal, ball);
+      s.brdf = albedo / PI_F;
+      s.pdf = 1.0f / (2.0f * PI_F);
+      break;
+    case RT_MAT_METAL:
+      s.ray.direction = reflect(ray.direction, hit.normal) + m.roughness * ball;
+      s.brdf = albedo;
+      s.pdf = 1.0f;
+      break;
+    case RT_MAT_DIELECTRIC: {
+      float eta = hit.frontface ? 1.0f / m.ior : m.ior;
+      float c = rmin(-dot(ray.direction, hit.normal), 1.0f);
+      bool critical_angle = eta * std::sqrt(1.0f - c * c) > 1.0f;
+      float fres = fresnel(ray.direction, hit.normal, m.ior);
+      bool will_refract = !critical_angle && u_choice >= fres;
+      s.ray.direction = will_refract ? refract(ray.direction, hit.normal, eta) : reflect(ray.direction, hit.normal);
+      s.brdf = v3(1.0f, 1.0f, 1.0f);
+      s.pdf = 1.0f;
+      break;
+    }
+    case RT_MAT_PARAMETERIZED: {
+      float fres = fresnel(ray.direction, hit.normal, 1.5f);
+      float k_s = fres * (1.0f - m.roughness);
+      float k_d = (1.0f - k_s) * (1.0f - m.metallic);
+      if (u_choice < k_d) {
+        s.ray.direction = sample_hemisphere(hit.normal, ball);
+        s.brdf = albedo / PI_F;
+        s.pdf = 1.0f / (2.0f * PI_F);
+      } else {
+        s.ray.direction = reflect(ray.direction, hit.normal) + m.roughness * ball;
+        s.brdf = lerpvec(v3(1.0f, 1.0f, 1.0f), albedo, m.metallic);
+        s.pdf = 1.0f;
+      }
+      break;
+    }
+    default:  // RT_MAT_ISOTROPIC
+      s.ray.direction = ball;
+      s.brdf = albedo;
+      s.pdf = 1.0f;
+      break;
+  }
+  return s;
+}
+
+struct RenderCtx {
+  const orc_scene* sc;
+  rt_camera cam;
+  int mode;
+  uint32_t k0, k1;
+};
+
+// Scene::shade_ray, tracing.rs:300-324 (path_samples == 1)
+V3 shade_ray(const RenderCtx& c, const Ray& ray, uint32_t depth, const RngKey& key, Counters* cnt) {
+  if (depth >= c.cam.path_depth) return v3(0, 0, 0);
+  Hit hit;
+  if (!scene_hit(*c.sc, ray, 0.001f, c.cam.max_trace_dist, c.mode, key, depth, hit, cnt)) return v3(0, 0, 0);
+  const rt_material_desc& m = hit.material >= 0 ? c.sc->materials[hit.material].d : hit.param;
+  U4 r = draw(key, depth, 0);
+  Scatter s = scatter(m, hit, ray, r);
+  float dot_term = mag2(hit.normal) > 0.0f ? rclamp(std::fabs(dot(s.ray.direction, hit.normal)), 0.0f, 1.0f) : 1.0f;
+  V3 incoming = shade_ray(c, s.ray, depth + 1, key, cnt);
+  V3 integral = (dot_term * mul_elem(s.brdf, incoming)) / s.pdf;
+  integral = integral / 1.0f;  // path_samples
+  V3 emission = m.tag == RT_MAT_DIELECTRIC ? v3(0, 0, 0) : v3(m.emission[0], m.emission[1], m.emission[2]);
+  return emission + integral;
+}
+
+// Camera::generate_rays for one sample index, tracing.rs:159-209 (perspective)
+inline Ray camera_ray(const rt_camera& cam, uint32_t sx, uint32_t sy, uint32_t i, const RngKey& key,
+                      float* offset_out) {
+  float pixel_size = 1.0f / (float)cam.screen_height;
+  float n = (float)cam.aa_sample_count;
+  float rootn = std::sqrt(n);
+  U4 r = draw(key, BOUNCE_CAMERA, 0);
+  // rng.gen_range(0..aa_sample_count)
+  float rand_x = (float)(uint32_t)(((uint64_t)r.v[0] * cam.aa_sample_count) >> 32);
+  float rand_y = (float)(uint32_t)(((uint64_t)r.v[1] * cam.aa_sample_count) >> 32);
+  uint32_t rooti = (uint32_t)rootn;
+  float subpixel_x = (float)(i / rooti);
+  float subpixel_y = (float)(i % rooti);
+  float off_x = (subpixel_x - 0.5f * rootn) * pixel_size / rootn + (rand_x - 0.5f * n) * pixel_size / n;
+  float off_y = (subpixel_y - 0.5f * rootn) * pixel_size / rootn + (rand_y - 0.5f * n) * pixel_size / n;
+  if (offset_out) {
+    offset_out[0] = off_x;
+    offset_out[1] = off_y;
+  }
+  V3 center = v3(pixel_size * ((float)sx - 0.5f * (float)cam.screen_width + 0.5f) + off_x,
+                 pixel_size * (0.5f + 0.5f * (float)cam.screen_height - (float)sy) + off_y, -cam.focal_length);
+  V3 focus = normalize(center) * cam.focus_dist;
+  V3 lens_origin = cam.lens_radius * disk_from(r.v[2], r.v[3]);
+  V3 view = v3(cam.view_dir[0], cam.view_dir[1], cam.view_dir[2]);
+  V3 up = v3(cam.up[0], cam.up[1], cam.up[2]);
+  V3 c0 = normalize(cross(view, up)), c1 = up, c2 = -view;
+  auto rot = [&](V3 v) { return c0 * v.x + c1 * v.y + c2 * v.z; };
+  Ray ray;
+  ray.origin = v3(cam.eyepoint[0], cam.eyepoint[1], cam.eyepoint[2]) + rot(lens_origin);
+  ray.direction = rot(normalize(focus - lens_origin));
+  return ray;
+}
+
+// tracing.rs:243-256
+inline void output_transform(V3 mean, float gamma, uint8_t* rgb) {
+  float fc[3] = {mean.x, mean.y, mean.z};
+  float tmp[3] = {mean.x, mean.y, mean.z};
+  for (int i = 0; i < 3; ++i) {
+    float d = tmp[i] - 1.0f;
+    if (d > 0.0f) {
+      fc[(i + 1) % 3] += d;
+      fc[(i + 2) % 3] += d;
+    }
+  }
+  for (int i = 0; i < 3; ++i) {
+    float v = std::pow(rclamp(fc[i], 0.0f, 1.0f), 1.0f / gamma) * 255.9999f;
+    rgb[i] = (v != v || v <= 0.0f) ? 0 : (v >= 255.0f ? 255 : (uint8_t)v);  // `as u8`
+  }
+}
+
+inline int check_camera(const rt_camera* cam) {
+  if (!cam) return RT_ERR_INVALID;
+  if (cam->projection_mode != RT_PROJ_PERSPECTIVE || cam->shading_mode != RT_SHADE_PATHTRACE) return RT_ERR_UNSUPPORTED;
+  if (cam->path_samples != 1) return RT_ERR_UNSUPPORTED;
+  if (cam->screen_width == 0 || cam->screen_height == 0 || cam->aa_sample_count == 0) return RT_ERR_INVALID;
+  return RT_OK;
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------- C ABI (orc_*)
+extern "C" {
+
+int orc_scene_create(orc_scene** out) {
+  if (!out) return RT_ERR_INVALID;
+  *out = new orc_scene();
+  return RT_OK;
+}
+void orc_scene_destroy(orc_scene* s) { delete s; }
+
+int orc_add_texture(orc_scene* s, const uint8_t* rgb8, uint32_t w, uint32_t h) {
+  if (!s || !rgb8 || !w || !h) return RT_ERR_INVALID;
+  Texture t;
+  t.w = w;
+  t.h = h;
+  t.rgb.assign(rgb8, rgb8 + (size_t)w * h * 3);
+  s->textures.push_back(std::move(t));
+  return (int)s->textures.size() - 1;
+}
+int orc_add_material(orc_scene* s, const rt_material_desc* d) {
+  if (!s || !d || d->tag > RT_MAT_ISOTROPIC) return RT_ERR_INVALID;
+  s->materials.push_back(Material{*d});
+  return (int)s->materials.size() - 1;
+}
+int orc_add_mesh(orc_scene* s, const float* pos, const float* nrm, const float* uv, uint32_t nverts,
+                 const uint32_t* idx, uint32_t ntris) {
+  if (!s || !pos || !nrm || !uv || !idx) return RT_ERR_INVALID;
+  for (uint32_t i = 0; i < 3 * ntris; ++i)
+    if (idx[i] >= nverts) return RT_ERR_INVALID;
+  auto m = std::make_unique<Mesh>();
+  m->pos.assign(pos, pos + 3 * (size_t)nverts);
+  m->nrm.assign(nrm, nrm + 3 * (size_t)nverts);
+  m->uv.assign(uv, uv + 2 * (size_t)nverts);
+  m->idx.assign(idx, idx + 3 * (size_t)ntris);
+  m->build_bvh();
+  // reachability for brute mode: a triangle under an interior node whose box has zero
+  // thickness on some axis is never reached (strict slab test)
+  std::vector<uint8_t> reach(ntris, 1);
+  struct Rec {
+    static void mark(const Mesh& m, int node, bool dead, std::vector<uint8_t>& reach) {
+      const Mesh::Node& n = m.nodes[node];
+      if (n.tri >= 0) {
+        if (dead) reach[n.tri] = 0;
+        return;
+      }
+      bool flat = n.box.min.x == n.box.max.x || n.box.min.y == n.box.max.y || n.box.min.z == n.box.max.z;
+      mark(m, n.left, dead || flat, reach);
+      mark(m, n.right, dead || flat, reach);
+    }
+  };
+  if (m->root >= 0) Rec::mark(*m, m->root, false, reach);
+  s->meshes.push_back(std::move(m));
+  s->reach.push_back(std::move(reach));
+  return (int)s->meshes.size() - 1;
+}
+int orc_mesh_reachability(orc_scene* s, int mesh, uint8_t* mask) {
+  if (!s || mesh < 0 || mesh >= (int)s->meshes.size() || !mask) return RT_ERR_INVALID;
+  std::memcpy(mask, s->reach[mesh].data(), s->reach[mesh].size());
+  return RT_OK;
+}
+int orc_add_instance(orc_scene* s, int mesh, const float xform[16], const float inv_xform[16], int material,
+                     const int tex[5]) {
+  if (!s || mesh < 0 || mesh >= (int)s->meshes.size() || !xform || !inv_xform) return RT_ERR_INVALID;
+  Object o;
+  o.kind = OBJ_MESH;
+  o.mesh = mesh;
+  std::memcpy(o.transform.m, xform, 64);
+  std::memcpy(o.inv_transform.m, inv_xform, 64);
+  o.material = material;
+  for (int i = 0; i < 5; ++i) o.tex[i] = tex ? tex[i] : -1;
+  s->objects.push_back(o);
+  return (int)s->objects.size() - 1;
+}
+int orc_add_sphere(orc_scene* s, const float c[3], float radius, int material) {
+  if (!s || !c) return RT_ERR_INVALID;
+  Object o;
+  o.kind = OBJ_SPHERE;
+  o.a = v3(c[0], c[1], c[2]);
+  o.radius = radius;
+  o.material = material;
+  s->objects.push_back(o);
+  return (int)s->objects.size() - 1;
+}
+int orc_add_triangle(orc_scene* s, const float a[3], const float b[3], const float c[3], int material) {
+  if (!s || !a || !b || !c) return RT_ERR_INVALID;
+  Object o;
+  o.kind = OBJ_TRIANGLE;
+  o.a = v3(a[0], a[1], a[2]);
+  o.b = v3(b[0], b[1], b[2]);
+  o.c = v3(c[0], c[1], c[2]);
+  o.material = material;
+  s->objects.push_back(o);
+  return (int)s->objects.size() - 1;
+}
+int orc_add_plane(orc_scene* s, const float p[3], const float n[3], int material) {
+  if (!s || !p || !n) return RT_ERR_INVALID;
+  Object o;
+  o.kind = OBJ_PLANE;
+  o.a = v3(p[0], p[1], p[2]);
+  o.b = v3(n[0], n[1], n[2]);
+  o.material = material;
+  s->objects.push_back(o);
+  return (int)s->objects.size() - 1;
+}
+int orc_add_volume_sphere(orc_scene* s, const float c[3], float radius, float density, int phase_material) {
+  if (!s || !c) return RT_ERR_INVALID;
+  Object o;
+  o.kind = OBJ_VOLUME;
+  o.a = v3(c[0], c[1], c[2]);
+  o.radius = radius;
+  o.density = density;
+  o.material = phase_material;
+  o.vol_index = s->n_volumes++;
+  s->objects.push_back(o);
+  return (int)s->objects.size() - 1;
+}
+
+// Scene::render_to_image, tracing.rs:221-263.  mode: 0 = reference tree, 1 = brute force.
+// Samples [sample_begin, sample_end) of every pixel; the mean divides by their count.
+int orc_render(const orc_scene* s, const rt_camera* cam, uint64_t seed, int mode, uint32_t sample_begin,
+               uint32_t sample_end, int nthreads, float* out_linear_rgb, uint8_t* out_rgb8, rt_stats* stats) {
+  int rc = check_camera(cam);
+  if (rc != RT_OK || !s) return rc != RT_OK ? rc : RT_ERR_INVALID;
+  if (sample_begin == 0 && sample_end == 0) sample_end = cam->aa_sample_count;
+  if (sample_end <= sample_begin || sample_end > cam->aa_sample_count) return RT_ERR_INVALID;
+  RenderCtx c{s, *cam, mode, (uint32_t)seed, (uint32_t)(seed >> 32)};
+  const uint32_t W = cam->screen_width, H = cam->screen_height;
+  uint64_t rays = 0, boxes = 0, tris = 0;
+#ifdef _OPENMP
+  if (nthreads > 0) omp_set_num_threads(nthreads);
+#endif
+#pragma omp parallel for schedule(dynamic, 1) reduction(+ : rays, boxes, tris)
+  for (int64_t y = 0; y < (int64_t)H; ++y) {
+    Counters cnt;
+    for (uint32_t x = 0; x < W; ++x) {
+      V3 final_color = v3(0, 0, 0);
+      uint32_t pixel = (uint32_t)y * W + x;
+      for (uint32_t i = sample_begin; i < sample_end; ++i) {
+        RngKey key{c.k0, c.k1, pixel, i};
+        Ray ray = camera_ray(*cam, x, (uint32_t)y, i, key, nullptr);
+        final_color = final_color + shade_ray(c, ray, 0, key, &cnt);
+      }
+      final_color = final_color / (float)(sample_end - sample_begin);
+      if (out_linear_rgb) {
+        out_linear_rgb[(size_t)pixel * 3 + 0] = final_color.x;
+        out_linear_rgb[(size_t)pixel * 3 + 1] = final_color.y;
+        out_linear_rgb[(size_t)pixel * 3 + 2] = final_color.z;
+      }
+      if (out_rgb8) output_transform(final_color, cam->gamma, out_rgb8 + (size_t)pixel * 3);
+    }
+    rays += cnt.rays;
+    boxes += cnt.box_tests;
+    tris += cnt.tri_tests;
+  }
+  if (stats) {
+    std::memset(stats, 0, sizeof *stats);
+    stats->samples = (uint64_t)W * H * (sample_end - sample_begin);
+    stats->rays = rays;
+    stats->nodes_visited = boxes;
+    stats->tris_tested = tris;
+  }
+  return RT_OK;
+}
+
+int orc_trace_primary(const orc_scene* s, const rt_camera* cam, uint64_t seed, int mode, uint32_t sample,
+                      int32_t* obj_id, int32_t* prim_id, float* t, float* normal_xyz, float* ray_od) {
+  int rc = check_camera(cam);
+  if (rc != RT_OK || !s) return rc != RT_OK ? rc : RT_ERR_INVALID;
+  const uint32_t W = cam->screen_width, H = cam->screen_height;
+#pragma omp parallel for schedule(dynamic, 4)
+  for (int64_t y = 0; y < (int64_t)H; ++y)
+    for (uint32_t x = 0; x < W; ++x) {
+      uint32_t pixel = (uint32_t)y * W + x;
+      RngKey key{(uint32_t)seed, (uint32_t)(seed >> 32), pixel, sample};
+      Ray ray = camera_ray(*cam, x, (uint32_t)y, sample, key, nullptr);
+      Hit h;
+      bool ok = scene_hit(*s, ray, 0.001f, cam->max_trace_dist, mode, key, 0, h, nullptr);
+      if (obj_id) obj_id[pixel] = ok ? h.obj : -1;
+      if (prim_id) prim_id[pixel] = ok ? h.prim : 0;
+      if (t) t[pixel] = ok ? h.distance : 0.0f;
+      if (normal_xyz) {
+        normal_xyz[pixel * 3 + 0] = ok ? h.normal.x : 0.0f;
+        normal_xyz[pixel * 3 + 1] = ok ? h.normal.y : 0.0f;
+        normal_xyz[pixel * 3 + 2] = ok ? h.normal.z : 0.0f;
+      }
+      if (ray_od) {
+        float* p = ray_od + (size_t)pixel * 6;
+        p[0] = ray.origin.x; p[1] = ray.origin.y; p[2] = ray.origin.z;
+        p[3] = ray.direction.x; p[4] = ray.direction.y; p[5] = ray.direction.z;
+      }
+    }
+  return RT_OK;
+}
+
+int orc_intersect_rays(const orc_scene* s, uint64_t seed, int mode, uint32_t n, const float* ray_od, float t_min,
+                       float t_max, int32_t* obj_id, int32_t* prim_id, float* t, float* normal_xyz,
+                       float* hitpoint_xyz, float* uv, int32_t* frontface) {
+  if (!s || !ray_od) return RT_ERR_INVALID;
+#pragma omp parallel for schedule(dynamic, 256)
+  for (int64_t i = 0; i < (int64_t)n; ++i) {
+    const float* p = ray_od + i * 6;
+    Ray ray{v3(p[0], p[1], p[2]), v3(p[3], p[4], p[5])};
+    RngKey key{(uint32_t)seed, (uint32_t)(seed >> 32), (uint32_t)i, 0};
+    Hit h;
+    bool ok = scene_hit(*s, ray, t_min, t_max, mode, key, 0, h, nullptr);
+    if (obj_id) obj_id[i] = ok ? h.obj : -1;
+    if (prim_id) prim_id[i] = ok ? h.prim : 0;
+    if (t) t[i] = ok ? h.distance : 0.0f;
+    if (frontface) frontface[i] = ok ? (h.frontface ? 1 : 0) : 0;
+    for (int k = 0; k < 3; ++k) {
+      if (normal_xyz) normal_xyz[i * 3 + k] = ok ? comp(h.normal, k) : 0.0f;
+      if (hitpoint_xyz) hitpoint_xyz[i * 3 + k] = ok ? comp(h.hitpoint, k) : 0.0f;
+    }
+    if (uv) {
+      uv[i * 2 + 0] = ok && h.has_uv ? h.u : 0.0f;
+      uv[i * 2 + 1] = ok && h.has_uv ? h.v : 0.0f;
+    }
+  }
+  return RT_OK;
+}
+
+// ---- probes for the known-answer tests
+// sub-pixel offsets (in units of pixel_size) of every sample of one pixel, tracing.rs:166-174
+int orc_camera_offsets(const rt_camera* cam, uint64_t seed, uint32_t x, uint32_t y, float* off_xy) {
+  int rc = check_camera(cam);
+  if (rc != RT_OK) return rc;
+  for (uint32_t i = 0; i < cam->aa_sample_count; ++i) {
+    RngKey key{(uint32_t)seed, (uint32_t)(seed >> 32), y * cam->screen_width + x, i};
+    float off[2];
+    camera_ray(*cam, x, y, i, key, off);
+    off_xy[i * 2 + 0] = off[0] * (float)cam->screen_height;
+    off_xy[i * 2 + 1] = off[1] * (float)cam->screen_height;
+  }
+  return RT_OK;
+}
+// n unit-ball and unit-disk samples from the RNG contract (pixel = i, sample 0, bounce 0)
+int orc_sample_ball_disk(uint64_t seed, uint32_t n, float* ball_xyz, float* disk_xy) {
+  for (uint32_t i = 0; i < n; ++i) {
+    U4 r = philox4x32_10(i, 0, 0, 0, (uint32_t)seed, (uint32_t)(seed >> 32));
+    V3 b = ball_from(r.v[1], r.v[2], r.v[3]);
+    V3 d = disk_from(r.v[2], r.v[3]);
+    if (ball_xyz) { ball_xyz[i * 3] = b.x; ball_xyz[i * 3 + 1] = b.y; ball_xyz[i * 3 + 2] = b.z; }
+    if (disk_xy) { disk_xy[i * 2] = d.x; disk_xy[i * 2 + 1] = d.y; }
+  }
+  return RT_OK;
+}
+int orc_philox(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1, uint32_t out[4]) {
+  U4 r = philox4x32_10(c0, c1, c2, c3, k0, k1);
+  std::memcpy(out, r.v, 16);
+  return RT_OK;
+}
+// hemisphere sample about `normal` from a ball point (materials.rs:171-178)
+int orc_sample_hemisphere(const float normal[3], const float ball[3], float out[3]) {
+  V3 d = sample_hemisphere(v3(normal[0], normal[1], normal[2]), v3(ball[0], ball[1], ball[2]));
+  out[0] = d.x; out[1] = d.y; out[2] = d.z;
+  return RT_OK;
+}
+int orc_texture_sample(const orc_scene* s, int tex, float u, float v, float out[3]) {
+  if (!s || tex < 0 || tex >= (int)s->textures.size()) return RT_ERR_INVALID;
+  V3 c = tex_sample(s->textures[tex], u, v);
+  out[0] = c.x; out[1] = c.y; out[2] = c.z;
+  return RT_OK;
+}
+int orc_output_transform(const float mean[3], float gamma, uint8_t rgb[3]) {
+  output_transform(v3(mean[0], mean[1], mean[2]), gamma, rgb);
+  return RT_OK;
+}
+int orc_num_threads(void) {
+#ifdef _OPENMP
+  return omp_get_max_threads();
+#else
+  return 1;
+#endif
+}
+
+}  // extern "C"
