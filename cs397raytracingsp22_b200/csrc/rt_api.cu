@@ -329,7 +329,8 @@ int run_wavefront(rt_scene* s, const rt_frame& fr_in, unsigned long long total, 
     stats->instances_entered += c.counters[2];
     stats->prims_tested += c.counters[3];
     stats->mesh_hits += c.counters[4];
-    stats->texel_taps += c.counters[5];
+    stats->texel_taps += c.counters[5] + c.counters[8];
+    stats->extend_texel_taps += c.counters[8];
     stats->material_fetches += c.counters[6];
     float ms = 0.0f;
     cudaEventElapsedTime(&ms, ev_begin, ev_end);

@@ -460,7 +460,7 @@ __device__ __forceinline__ void resolve_hit(const rt_dev_scene& sc, f3 wo, f3 wd
       f3 bitangent = normalize(cross(n, tan));
       f3 tangent = normalize(cross(bitangent, n));
       f3 smp = tex_sample(sc, tex_normal, s.u, s.v);
-      if (COUNT) atomicAdd(&counters[5], 1ull);
+      if (COUNT) atomicAdd(&counters[8], 1ull);
       f3 nm = 2.0f * smp - mk(1.0f, 1.0f, 1.0f);
       n = tangent * nm.x + bitangent * nm.y + n * nm.z;
     }
@@ -869,7 +869,7 @@ __global__ void k_init_ctrl(rt_ctrl* c, unsigned long long total) {
   for (int i = 0; i < RT_NUM_CLASSES; ++i) c->class_count[i] = 0;
   c->done = 0;
   c->iterations = 0;
-  for (int i = 0; i < 8; ++i) c->counters[i] = 0;
+  for (int i = 0; i < 10; ++i) c->counters[i] = 0;
 }
 // stats that k_advance cannot see until the iteration has run
 __global__ void k_tally(rt_ctrl* c) {

@@ -74,7 +74,8 @@ struct rt_ctrl {
   uint32_t done;                   // 1 when cursor==total and nothing is in flight
   uint32_t iterations;
   uint32_t pad_;
-  unsigned long long counters[8];  // nodes, tris, instances, prims, mesh_hits, taps, mats, invalid tile slots
+  unsigned long long counters[10]; // nodes, tris, instances, prims, mesh_hits, shade taps, mats, invalid tile slots,
+                                   // normal-map taps (k_extend), -
 };
 
 struct rt_frame {

@@ -119,7 +119,8 @@ typedef struct rt_stats {
   uint64_t instances_entered; /* 96 bytes of transforms fetched                     */
   uint64_t prims_tested;      /* analytic sphere/triangle/plane/volume records      */
   uint64_t mesh_hits;         /* 80-byte shading records fetched                    */
-  uint64_t texel_taps;        /* RGB8 texel fetches                                 */
+  uint64_t texel_taps;        /* RGB8 texel fetches (all kernels)                   */
+  uint64_t extend_texel_taps; /* of those, normal-map taps made inside k_extend     */
   uint64_t material_fetches;  /* 32-byte material records fetched                   */
   /* CUDA-event times on the render stream, milliseconds */
   double ms_total;
