@@ -173,9 +173,16 @@ __device__ __forceinline__ uint32_t pack_entry(float4 lo, float4 hi) {
   uint32_t lf = fbits(lo.w), cnt = fbits(hi.w);
   return cnt ? (RT_LEAF_FLAG | (lf << 4) | cnt) : lf;
 }
-__device__ __forceinline__ f3 approx_inv(f3 d) {
-  return mk(__fdividef(1.0f, d.x), __fdividef(1.0f, d.y), __fdividef(1.0f, d.z));
+// reciprocal direction for the slab tests only.  A component that is exactly (or nearly) zero is
+// replaced by +-1e-20 so that lo*inv + oi never becomes inf - inf: the slab then yields two huge
+// finite values of the right signs and does not constrain the interval, which is what a ray
+// parallel to (and inside) the slab needs.  Camera rays through the image centre column have
+// d.x == 0 exactly, so this case is routine, not exotic.
+__device__ __forceinline__ float safe_rcp(float d) {
+  float a = fabsf(d) < 1e-20f ? copysignf(1e-20f, d) : d;
+  return __fdividef(1.0f, a);
 }
+__device__ __forceinline__ f3 approx_inv(f3 d) { return mk(safe_rcp(d.x), safe_rcp(d.y), safe_rcp(d.z)); }
 
 // Sphere::intersect_ray core (geometry.rs:397-410): returns t or NaN-free miss flag
 __device__ __forceinline__ bool sphere_t(f3 center, float radius, f3 o, f3 d, float t_min, float t_max, float& t) {

@@ -144,7 +144,9 @@ def test_low_spp_images_track_the_oracle_sample_for_sample(gpu, small_scenes, na
     sc = small_scenes(name)
     lin_g, rgb_g, st_g, lin_o, rgb_o, st_o = _render_pair(sc)
     assert st_g.samples == st_o.samples
-    assert abs(int(st_g.rays) - int(st_o.rays)) <= 0.01 * st_o.rays        # zero-throughput paths end early on the GPU
+    # the GPU drops a path once its throughput is exactly zero (it can add nothing any more: e.g. after the
+    # albedo-0 volume of c4), so it issues at most as many closest-hit queries as the reference does
+    assert st_g.rays <= st_o.rays * 1.001 and st_g.rays >= 0.9 * st_o.rays
     diff = np.abs(lin_g - lin_o)
     scale = max(float(lin_o.mean()), 1e-6)
     assert np.median(diff) <= 1e-5 * max(scale, 1.0)
