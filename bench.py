@@ -355,6 +355,7 @@ def main():
         "bytes_per_ray": extend_algorithmic_bytes(counted) / max(counted["rays"], 1),
         "nodes_per_ray": counted["nodes_visited"] / max(counted["rays"], 1),
         "tris_per_ray": counted["tris_tested"] / max(counted["rays"], 1),
+        "traversal_simt_efficiency": counted["nodes_visited"] / max(counted["warp_node_slots"], 1),
         "note": "the lowered scene fits in L2, so DRAM traffic is far below algorithmic bytes; the kernel is "
                 "latency/issue bound (see profiles/)",
     }

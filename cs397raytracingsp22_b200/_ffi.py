@@ -53,7 +53,7 @@ class rt_stats(C.Structure):
     _fields_ = [(n, C.c_uint64) for n in (
         "samples", "rays", "iterations", "kernel_launches", "extend_launches", "shade_launches", "nodes_visited",
         "tris_tested", "instances_entered", "prims_tested", "mesh_hits", "texel_taps", "extend_texel_taps",
-        "material_fetches")] + [
+        "material_fetches", "warp_node_slots")] + [
         (n, C.c_double) for n in ("ms_total", "ms_extend", "ms_shade", "ms_resolve")] + [
         ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64)]
 

@@ -16,7 +16,7 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-LIB = os.path.join(HERE, "librt_b200.so")
+LIB = os.environ.get("RT_B200_LIB") or os.path.join(HERE, "librt_b200.so")  # RT_B200_LIB: A/B builds
 SOURCES = ["rt_kernels.cu", "rt_api.cu", "rt_lower.cpp"]
 HEADERS = ["rt_kernels.h", "rt_lower.h", "rt_types.h", os.path.join("..", "..", "include", "rt_b200.h")]
 
@@ -41,8 +41,9 @@ def needs_build() -> bool:
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    if not force and not needs_build():
+def build(force: bool = False, verbose: bool = False, defines: tuple = (), out: str | None = None) -> str:
+    out = out or LIB
+    if not force and not needs_build() and out == LIB:
         return LIB
     cmd = [
         _nvcc(), *_host_cxx(),
@@ -50,7 +51,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
         "-lineinfo", "-O3", "-std=c++17",
         "-fmad=false",
         "-Xcompiler", "-fPIC,-ffp-contract=off,-fno-fast-math,-O3",
-        "-shared", "-o", LIB,
+        *[f"-D{d}" for d in defines],
+        "-shared", "-o", out,
         *[os.path.join(CSRC, f) for f in SOURCES],
     ]
     if verbose:
@@ -61,8 +63,10 @@ def build(force: bool = False, verbose: bool = False) -> str:
         raise RuntimeError("nvcc failed:\n" + r.stdout + r.stderr)
     if verbose:
         print(r.stderr, file=sys.stderr)
-    return LIB
+    return out
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose=True))
+    defs = tuple(a[2:] for a in sys.argv[1:] if a.startswith("-D"))
+    outs = [a[6:] for a in sys.argv[1:] if a.startswith("--out=")]
+    print(build(force=True, verbose="-v" in sys.argv, defines=defs, out=outs[0] if outs else None))

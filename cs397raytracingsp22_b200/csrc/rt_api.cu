@@ -60,6 +60,7 @@ struct rt_scene {
   cudaEvent_t poll_ev[2] = {nullptr, nullptr};
   std::vector<cudaEvent_t> events;
   cudaStream_t own_stream = nullptr;
+  uint32_t persistent_blocks = 148 * 8;  // k_extend grid: SM count x resident blocks per SM
   // scratch for host-buffer entry points
   DevBuf d_accum, d_linear, d_rgb8, d_dbg;
 };
@@ -92,9 +93,8 @@ void free_wavefront(rt_scene* s) {
     if (s->paths[k].C) cudaFree(s->paths[k].C);
     s->paths[k] = rt::rt_paths{};
   }
-  if (s->hits.H0) cudaFree(s->hits.H0);
-  if (s->hits.H1) cudaFree(s->hits.H1);
-  if (s->hits.H2) cudaFree(s->hits.H2);
+  if (s->hits.H) cudaFree(s->hits.H);
+  if (s->hits.obj) cudaFree(s->hits.obj);
   s->hits = rt::rt_hits{};
   if (s->queues) cudaFree(s->queues);
   s->queues = nullptr;
@@ -109,6 +109,9 @@ int ensure_wavefront(rt_scene* s, uint32_t capacity) {
     CUDA_TRY(cudaEventCreateWithFlags(&s->poll_ev[0], cudaEventDisableTiming));
     CUDA_TRY(cudaEventCreateWithFlags(&s->poll_ev[1], cudaEventDisableTiming));
     CUDA_TRY(cudaStreamCreateWithFlags(&s->own_stream, cudaStreamNonBlocking));
+    int sms = 0;
+    CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, s->device));
+    s->persistent_blocks = (uint32_t)(sms * rt::trace_blocks_per_sm());
   }
   if (s->capacity >= capacity && s->queues) return RT_OK;
   free_wavefront(s);
@@ -118,9 +121,8 @@ int ensure_wavefront(rt_scene* s, uint32_t capacity) {
     CUDA_TRY(cudaMalloc((void**)&s->paths[k].B, n * 16));
     CUDA_TRY(cudaMalloc((void**)&s->paths[k].C, n * 16));
   }
-  CUDA_TRY(cudaMalloc((void**)&s->hits.H0, n * 16));
-  CUDA_TRY(cudaMalloc((void**)&s->hits.H1, n * 16));
-  CUDA_TRY(cudaMalloc((void**)&s->hits.H2, n * 4));
+  CUDA_TRY(cudaMalloc((void**)&s->hits.H, n * 16));
+  CUDA_TRY(cudaMalloc((void**)&s->hits.obj, n * 4));
   CUDA_TRY(cudaMalloc((void**)&s->queues, n * 4 * RT_NUM_CLASSES));
   s->capacity = capacity;
   return RT_OK;
@@ -242,8 +244,8 @@ int set_device(rt_scene* s) {
 // iteration has.  The host only peeks at a `done` flag every few iterations, two polls deep, so
 // the stream never drains.
 int run_wavefront(rt_scene* s, const rt_frame& fr_in, unsigned long long total, long long* d_accum, bool count,
-                  bool debug, rt::rt_debug dbg, bool single_iteration, bool use_events, cudaStream_t st,
-                  rt_stats* stats) {
+                  bool use_events, cudaStream_t st, rt_stats* stats) {
+  const bool single_iteration = false;
   rt_frame fr = fr_in;
   int rc = ensure_wavefront(s, fr.capacity);
   if (rc != RT_OK) return rc;
@@ -284,9 +286,9 @@ int run_wavefront(rt_scene* s, const rt_frame& fr_in, unsigned long long total, 
         if ((rc = next_event(e0)) != RT_OK || (rc = next_event(e1)) != RT_OK || (rc = next_event(e2)) != RT_OK) return rc;
         CUDA_TRY(cudaEventRecord(e0, st));
       }
-      rt::launch_extend(s->dev, fr, s->ctrl, s->paths[cur], s->hits, s->queues, dbg, count, debug, st);
+      rt::launch_extend(s->dev, fr, s->ctrl, s->paths[cur], s->hits, s->queues, count, true, s->persistent_blocks, st);
       if (timed) CUDA_TRY(cudaEventRecord(e1, st));
-      ++launches; ++ext_launches;
+      launches += 3; ++ext_launches;
       if (!single_iteration) {
         rt::launch_shade(s->dev, fr, s->ctrl, s->paths[cur], s->paths[nxt], s->hits, s->queues, d_accum, count, st);
         ++launches; ++shd_launches;
@@ -332,6 +334,7 @@ int run_wavefront(rt_scene* s, const rt_frame& fr_in, unsigned long long total, 
     stats->texel_taps += c.counters[5] + c.counters[8];
     stats->extend_texel_taps += c.counters[8];
     stats->material_fetches += c.counters[6];
+    stats->warp_node_slots += c.counters[9];
     float ms = 0.0f;
     cudaEventElapsedTime(&ms, ev_begin, ev_end);
     stats->ms_total += ms;
@@ -571,8 +574,7 @@ int rt_render_accum(rt_scene* s, const rt_camera* cam, const rt_render_opts* opt
     if ((rc = ensure_wavefront(s, fr.capacity)) != RT_OK) return rc;
     st = s->own_stream;
   }
-  rt::rt_debug dbg{nullptr, nullptr, nullptr};
-  return run_wavefront(s, fr, total, (long long*)d_accum, (o.flags & RT_OPT_COUNTERS) != 0, false, dbg, false,
+  return run_wavefront(s, fr, total, (long long*)d_accum, (o.flags & RT_OPT_COUNTERS) != 0,
                        (o.flags & RT_OPT_NO_EVENTS) == 0, st, stats);
 }
 
@@ -645,11 +647,12 @@ static int trace_common(rt_scene* s, const rt_frame& fr, unsigned long long tota
   int rc = ensure_wavefront(s, fr.capacity);
   if (rc != RT_OK) return rc;
   cudaStream_t st = s->own_stream;
-  if ((rc = ensure_buf(s->d_dbg, (size_t)n * 12)) != RT_OK) return rc;
+  const size_t cap = fr.capacity;
+  if ((rc = ensure_buf(s->d_dbg, cap * 36)) != RT_OK) return rc;
   rt::rt_debug dbg;
-  dbg.obj = (int32_t*)s->d_dbg.p;
-  dbg.prim = dbg.obj + n;
-  dbg.t = (float*)(dbg.prim + n);
+  dbg.S0 = (float4*)s->d_dbg.p;
+  dbg.S1 = dbg.S0 + cap;
+  dbg.S2 = (uint32_t*)(dbg.S1 + cap);
   std::vector<float> A, B, C;
   if (ray_od) {
     // caller-supplied rays become "continuing" rays: pixel = i, sample 0, bounce 0
@@ -673,18 +676,18 @@ static int trace_common(rt_scene* s, const rt_frame& fr, unsigned long long tota
   rt::launch_init(s->ctrl, ray_od ? 0ull : total, st);
   if (ray_od) CUDA_TRY(cudaMemcpyAsync(&s->ctrl->n_next, &n, 4, cudaMemcpyHostToDevice, st));
   rt::launch_advance(s->ctrl, f2.capacity, st);
-  rt::launch_extend(s->dev, f2, s->ctrl, s->paths[0], s->hits, s->queues, dbg, false, true, st);
+  rt::launch_extend(s->dev, f2, s->ctrl, s->paths[0], s->hits, s->queues, false, ray_od == nullptr, s->persistent_blocks, st);
+  rt::launch_surface(s->dev, f2, s->ctrl, s->paths[0], s->hits, dbg, st);
   CUDA_TRY(cudaGetLastError());
-  std::vector<float> H0((size_t)n * 4), H1((size_t)n * 4);
+  std::vector<float> H0((size_t)n * 4), H1((size_t)n * 4), HH((size_t)n * 4);
   std::vector<uint32_t> H2(n);
   std::vector<int32_t> o(n), p(n);
   std::vector<float> tt(n);
-  CUDA_TRY(cudaMemcpyAsync(H0.data(), s->hits.H0, (size_t)n * 16, cudaMemcpyDeviceToHost, st));
-  CUDA_TRY(cudaMemcpyAsync(H1.data(), s->hits.H1, (size_t)n * 16, cudaMemcpyDeviceToHost, st));
-  CUDA_TRY(cudaMemcpyAsync(H2.data(), s->hits.H2, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
-  CUDA_TRY(cudaMemcpyAsync(o.data(), dbg.obj, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
-  CUDA_TRY(cudaMemcpyAsync(p.data(), dbg.prim, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
-  CUDA_TRY(cudaMemcpyAsync(tt.data(), dbg.t, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaMemcpyAsync(H0.data(), dbg.S0, (size_t)n * 16, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaMemcpyAsync(H1.data(), dbg.S1, (size_t)n * 16, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaMemcpyAsync(H2.data(), dbg.S2, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaMemcpyAsync(HH.data(), s->hits.H, (size_t)n * 16, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaMemcpyAsync(o.data(), s->hits.obj, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
   if (ray_out) {
     A.resize((size_t)n * 4); B.resize((size_t)n * 4);
     CUDA_TRY(cudaMemcpyAsync(A.data(), s->paths[0].A, (size_t)n * 16, cudaMemcpyDeviceToHost, st));
@@ -693,6 +696,10 @@ static int trace_common(rt_scene* s, const rt_frame& fr, unsigned long long tota
   CUDA_TRY(cudaStreamSynchronize(st));
   for (uint32_t i = 0; i < n; ++i) {
     bool hit = o[i] >= 0;
+    tt[i] = hit ? HH[4 * i] : 0.0f;
+    uint32_t pr;
+    std::memcpy(&pr, &HH[4 * i + 3], 4);
+    p[i] = hit ? (int32_t)pr : 0;
     if (obj_id) obj_id[i] = o[i];
     if (prim_id) prim_id[i] = p[i];
     if (t) t[i] = tt[i];

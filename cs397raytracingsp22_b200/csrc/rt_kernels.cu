@@ -1,12 +1,14 @@
 // rt_kernels.cu — hand-written sm_100a kernels of the wavefront path tracer.
 //
 //   k_advance : 1 thread; wavefront bookkeeping between bounces (device-side, no host sync)
-//   k_extend  : ray-gen (Camera::generate_rays, tracing.rs:159-209) fused with the closest-hit
-//               query (Scene::intersect_ray tracing.rs:327-346 and everything under it:
-//               geometry.rs:50-123,300-366,394-526), hit resolution (geometry.rs:253-298,350-363)
-//               and material-sorted enqueue (match/ballot compaction)
-//   k_shade   : Material::scatter / emission (materials.rs:33-166) + the integrator step of
-//               Scene::shade_ray (tracing.rs:300-324), one warp-uniform material class per warp
+//   k_raygen  : Camera::generate_rays (tracing.rs:159-209) for the paths started this iteration
+//   k_trace   : closest hit (Scene::intersect_ray tracing.rs:327-346 and everything under it:
+//               geometry.rs:50-123,300-366,394-526).  Persistent warps with dynamic ray fetch.
+//   k_sort    : material-sorted shade queues (match/ballot compaction)
+//   k_shade   : hit resolution (RayHit::new tracing.rs:121-133, geometry.rs:253-298,350-363),
+//               Material::scatter / emission (materials.rs:33-166) and the integrator step of
+//               Scene::shade_ray (tracing.rs:300-324); one warp-uniform material class per warp
+//   k_surface : parity hooks only: hit resolution for every ray, written out
 //   k_resolve : mean + output transform (tracing.rs:241-256)
 //
 // Arithmetic contract: this file is compiled with -fmad=false.  Everything that decides WHICH
@@ -29,6 +31,9 @@ namespace rt {
 #define RT_WARPS (RT_BLOCK / 32)
 #define RT_SMEM_STACK 16   // traversal-stack entries per thread kept in shared memory
 #define RT_LOCAL_STACK 48  // overflow entries (local memory; host checks depth <= 62)
+#ifndef RT_EXTEND_MIN_BLOCKS
+#define RT_EXTEND_MIN_BLOCKS 8  // 64 registers per thread -> 32 resident warps per SM
+#endif
 
 // ------------------------------------------------------------------ small vector helpers
 struct f3 {
@@ -146,7 +151,7 @@ struct Best {
   uint32_t prim; // original triangle index inside the mesh
 };
 struct Cnt {
-  uint32_t nodes, tris, inst, prims;
+  uint32_t nodes, tris, inst, prims, rounds;
 };
 
 // reference ordering of candidates: smaller t wins; equal t: earlier object wins (strict '<' in
@@ -168,10 +173,6 @@ __device__ __forceinline__ bool slab(float4 lo, float4 hi, f3 inv, f3 oi, float 
   float b = fminf(fminf(fmaxf(x0, x1), fmaxf(y0, y1)), fminf(fmaxf(z0, z1), tmax));
   tn = a;
   return a <= b * 1.0000005f;
-}
-__device__ __forceinline__ uint32_t pack_entry(float4 lo, float4 hi) {
-  uint32_t lf = fbits(lo.w), cnt = fbits(hi.w);
-  return cnt ? (RT_LEAF_FLAG | (lf << 4) | cnt) : lf;
 }
 // reciprocal direction for the slab tests only.  A component that is exactly (or nearly) zero is
 // replaced by +-1e-20 so that lo*inv + oi never becomes inf - inf: the slab then yields two huge
@@ -199,197 +200,209 @@ __device__ __forceinline__ bool sphere_t(f3 center, float radius, f3 o, f3 d, fl
   return !(t < t_min || t > t_max);
 }
 
-template <bool COUNT>
-__device__ __forceinline__ void closest_hit(const rt_dev_scene& sc, f3 wo, f3 wd, float t_min, float t_max,
-                                            uint32_t k0, uint32_t k1, uint32_t pixel, uint32_t sample,
-                                            uint32_t bounce, uint32_t* sstack, Best& best, Cnt& cnt) {
-  best.t = t_max;
-  best.obj = -1;
-  best.prim = 0;
-  best.u = best.v = 0.0f;
-  uint32_t lstack[RT_LOCAL_STACK];
-  int sp = 0;
-  const uint32_t tid = threadIdx.x;
-#define RT_PUSH(val)                                        \
-  do {                                                      \
-    if (sp < RT_SMEM_STACK) sstack[sp * RT_BLOCK + tid] = (val); \
-    else lstack[sp - RT_SMEM_STACK] = (val);                \
-    ++sp;                                                   \
-  } while (0)
-#define RT_POP(dst)                                         \
-  do {                                                      \
-    --sp;                                                   \
-    (dst) = sp < RT_SMEM_STACK ? sstack[sp * RT_BLOCK + tid] : lstack[sp - RT_SMEM_STACK]; \
-  } while (0)
-
-  f3 o = wo, d = wd;
-  f3 inv = approx_inv(d);
-  f3 oi = mk(-o.x * inv.x, -o.y * inv.y, -o.z * inv.z);
-  bool in_blas = false;
-  int cur_obj = -1;
-  uint32_t entry = sc.tlas_root;
-  if (entry != RT_ENTRY_NONE) {
-    float tn;
-    float4 lo = make_float4(sc.tlas_min[0], sc.tlas_min[1], sc.tlas_min[2], 0.0f);
-    float4 hi = make_float4(sc.tlas_max[0], sc.tlas_max[1], sc.tlas_max[2], 0.0f);
-    if (!slab(lo, hi, inv, oi, t_min, t_max, tn)) entry = RT_ENTRY_NONE;
+// per-ray traversal state.  The short stack lives in shared memory ([depth][thread], conflict
+// free); entries beyond RT_SMEM_STACK spill to a local-memory array that is almost never touched.
+struct Trav {
+  // The world-space ray and the RNG key are NOT kept in registers: they stay in the ray queue
+  // (slot `slot` of A/B/C) and are re-read on the rare occasions they are needed (leaving an
+  // instance, TLAS object tests, volume draws, hit resolution).  That keeps the persistent state
+  // of k_extend small enough for 7-8 resident blocks per SM.
+  const float4* qA;
+  const float4* qB;
+  const float4* qC;
+  uint32_t slot;
+  f3 o, d, inv, oi; // current-space ray (world or instance), reciprocal direction, -o*inv
+  float t_min, t_max;
+  uint32_t entry;   // packed node link being visited, RT_ENTRY_NONE when a pop is needed
+  int sp;
+  int cur_obj;
+  bool in_blas;
+  uint32_t* sstack;
+  uint32_t* lstack;  // RT_LOCAL_STACK entries of local memory, declared by the kernel
+  Best best;
+  Cnt cnt;
+  uint32_t k0, k1;  // Philox key (kernel constants)
+  __device__ __forceinline__ void world_ray(f3& wo, f3& wd) const {
+    float4 a = qA[slot], b = qB[slot];
+    wo = mk(a.x, a.y, a.z);
+    wd = mk(a.w, b.x, b.y);
   }
 
-  for (;;) {
-    // descend interior nodes: fetch the 64-byte child pair with four 128-bit read-only loads
-    while (entry != RT_ENTRY_NONE && !(entry & RT_LEAF_FLAG)) {
-      float4 l0 = ldq(sc.nodes, entry * 2u), l1 = ldq(sc.nodes, entry * 2u + 1u);
-      float4 r0 = ldq(sc.nodes, entry * 2u + 2u), r1 = ldq(sc.nodes, entry * 2u + 3u);
-      if (COUNT) cnt.nodes += 2;
-      float tl, tr;
-      bool hl = slab(l0, l1, inv, oi, t_min, best.t, tl);
-      bool hr = slab(r0, r1, inv, oi, t_min, best.t, tr);
-      uint32_t el = pack_entry(l0, l1), er = pack_entry(r0, r1);
-      if (hl && hr) {
-        bool lfirst = tl <= tr;
-        RT_PUSH(lfirst ? er : el);
-        entry = lfirst ? el : er;
-      } else {
-        entry = hl ? el : (hr ? er : RT_ENTRY_NONE);
-      }
-    }
-    if (entry != RT_ENTRY_NONE) {
-      uint32_t first = (entry & ~RT_LEAF_FLAG) >> 4, n = entry & 15u;
+  __device__ __forceinline__ void push(uint32_t v) {
+    if (sp < RT_SMEM_STACK) sstack[sp * RT_BLOCK + threadIdx.x] = v;
+    else lstack[sp - RT_SMEM_STACK] = v;
+    ++sp;
+  }
+  __device__ __forceinline__ uint32_t pop() {
+    --sp;
+    return sp < RT_SMEM_STACK ? sstack[sp * RT_BLOCK + threadIdx.x] : lstack[sp - RT_SMEM_STACK];
+  }
+  __device__ __forceinline__ void set_space(f3 no, f3 nd) {
+    o = no; d = nd;
+    inv = approx_inv(d);
+    oi = mk(-o.x * inv.x, -o.y * inv.y, -o.z * inv.z);
+  }
+  // pop the next entry; false when the stack is empty.  A RESTORE marker switches back to the
+  // world-space ray and leaves entry = NONE (the caller pops again).
+  __device__ __forceinline__ bool pop_next() {
+    if (sp == 0) return false;
+    entry = pop();
+    if (entry == RT_ENTRY_RESTORE) {
+      f3 wo, wd;
+      world_ray(wo, wd);
+      set_space(wo, wd);
+      in_blas = false;
       entry = RT_ENTRY_NONE;
-      if (in_blas) {
-        // IndexedTriangle::intersect_ray, geometry.rs:333-349 (object space, un-normalised d)
-        for (uint32_t k = 0; k < n; ++k) {
-          uint32_t q = (first + k) * RT_TRI_QUADS;
-          float4 a0 = ldq(sc.tris, q), a1 = ldq(sc.tris, q + 1), a2 = ldq(sc.tris, q + 2);
-          if (COUNT) cnt.tris += 1;
-          f3 va = mk(a0.x, a0.y, a0.z), e1 = mk(a0.w, a1.x, a1.y), e2 = mk(a1.z, a1.w, a2.x);
-          f3 qv = cross(d, e2);
-          float g = dot(e1, qv);
-          if (fabsf(g) < 0.0001f) continue;
-          float f = 1.0f / g;
-          f3 s = o - va;
-          float u = f * dot(s, qv);
-          if (u < 0.0f) continue;
-          f3 r = cross(s, e1);
-          float v = f * dot(d, r);
-          if (v < 0.0f || u + v > 1.0f) continue;
+    }
+    return true;
+  }
+};
+
+// interior node: fetch the 64-byte child pair with four 128-bit read-only loads, test both boxes,
+// continue with the nearer child and push the other
+template <bool COUNT>
+__device__ __forceinline__ void trav_interior(const rt_dev_scene& sc, Trav& T) {
+  uint32_t e = T.entry;
+  float4 l0 = ldq(sc.nodes, e * 2u), l1 = ldq(sc.nodes, e * 2u + 1u);
+  float4 r0 = ldq(sc.nodes, e * 2u + 2u), r1 = ldq(sc.nodes, e * 2u + 3u);
+  if (COUNT) T.cnt.nodes += 2;
+  float tl, tr;
+  bool hl = slab(l0, l1, T.inv, T.oi, T.t_min, T.best.t, tl);
+  bool hr = slab(r0, r1, T.inv, T.oi, T.t_min, T.best.t, tr);
+  uint32_t el = fbits(l0.w), er = fbits(r0.w);
+  if (hl && hr) {
+    bool lfirst = tl <= tr;
+    T.push(lfirst ? er : el);
+    T.entry = lfirst ? el : er;
+  } else {
+    T.entry = hl ? el : (hr ? er : RT_ENTRY_NONE);
+  }
+}
+
+// leaf: BLAS leaf = up to RT_MAX_LEAF_TRIS triangle records; TLAS leaf = one top-level object
+template <bool COUNT>
+__device__ __forceinline__ void trav_leaf(const rt_dev_scene& sc, Trav& T) {
+  const uint32_t first = (T.entry & ~RT_LEAF_FLAG) >> 4, n = T.entry & 15u;
+  const float t_min = T.t_min, t_max = T.t_max;
+  Best& best = T.best;
+  T.entry = RT_ENTRY_NONE;
+  if (T.in_blas) {
+    // IndexedTriangle::intersect_ray, geometry.rs:333-349 (object space, un-normalised d)
+    const f3 o = T.o, d = T.d;
+    for (uint32_t k = 0; k < n; ++k) {
+      uint32_t q = (first + k) * RT_TRI_QUADS;
+      float4 a0 = ldq(sc.tris, q), a1 = ldq(sc.tris, q + 1), a2 = ldq(sc.tris, q + 2);
+      if (COUNT) T.cnt.tris += 1;
+      f3 va = mk(a0.x, a0.y, a0.z), e1 = mk(a0.w, a1.x, a1.y), e2 = mk(a1.z, a1.w, a2.x);
+      f3 qv = cross(d, e2);
+      float g = dot(e1, qv);
+      if (fabsf(g) < 0.0001f) continue;
+      float f = 1.0f / g;
+      f3 s = o - va;
+      float u = f * dot(s, qv);
+      if (u < 0.0f) continue;
+      f3 r = cross(s, e1);
+      float v = f * dot(d, r);
+      if (v < 0.0f || u + v > 1.0f) continue;
+      float t = f * dot(e2, r);
+      if (t < t_min || t > t_max) continue;
+      uint32_t id = fbits(a2.y);
+      if (better(t, T.cur_obj, id, best)) {
+        best.t = t; best.u = u; best.v = v; best.obj = T.cur_obj; best.prim = id;
+      }
+    }
+    return;
+  }
+  const f3 wo = T.o, wd = T.d;  // not inside an instance: the current space IS world space
+  int obj = (int)first;
+  uint32_t q = (uint32_t)obj * RT_OBJ_QUADS;
+  float4 h = ldq(sc.objects, q);
+  int kind = (int)fbits(h.x);
+  if (kind == RT_OBJ_MESH) {
+    float4 r0 = ldq(sc.objects, q + 1), r1 = ldq(sc.objects, q + 2), r2 = ldq(sc.objects, q + 3);
+    float4 m7 = ldq(sc.objects, q + 7);
+    if (COUNT) T.cnt.inst += 1;
+    // StaticMesh::intersect_ray, geometry.rs:304: transform_point / transform_vector
+    f3 no = mk(r0.x * wo.x + r0.y * wo.y + r0.z * wo.z + r0.w * 1.0f, r1.x * wo.x + r1.y * wo.y + r1.z * wo.z + r1.w * 1.0f,
+               r2.x * wo.x + r2.y * wo.y + r2.z * wo.z + r2.w * 1.0f);
+    f3 nd = mk(r0.x * wd.x + r0.y * wd.y + r0.z * wd.z + r0.w * 0.0f, r1.x * wd.x + r1.y * wd.y + r1.z * wd.z + r1.w * 0.0f,
+               r2.x * wd.x + r2.y * wd.y + r2.z * wd.z + r2.w * 0.0f);
+    uint32_t root = fbits(m7.x);
+    if (root != RT_ENTRY_NONE) {
+      T.push(RT_ENTRY_RESTORE);
+      T.set_space(no, nd);
+      T.in_blas = true;
+      T.cur_obj = obj;
+      T.entry = root;
+    }
+    return;
+  }
+  if (COUNT) T.cnt.prims += 1;
+  float4 q1 = ldq(sc.objects, q + 1);
+  if (kind == RT_OBJ_SPHERE) {
+    float t;
+    if (sphere_t(mk(q1.x, q1.y, q1.z), q1.w, wo, wd, t_min, t_max, t) && better(t, obj, 0u, best)) {
+      best.t = t; best.obj = obj; best.prim = 0;
+    }
+  } else if (kind == RT_OBJ_TRIANGLE) {
+    // Triangle::intersect_ray, geometry.rs:433-447
+    float4 q2 = ldq(sc.objects, q + 2), q3 = ldq(sc.objects, q + 3);
+    f3 va = mk(q1.x, q1.y, q1.z), e1 = mk(q1.w, q2.x, q2.y), e2 = mk(q2.z, q2.w, q3.x);
+    f3 qv = cross(wd, e2);
+    float g = dot(e1, qv);
+    if (!(fabsf(g) < 0.0001f)) {
+      float f = 1.0f / g;
+      f3 s = wo - va;
+      float u = f * dot(s, qv);
+      if (!(u < 0.0f)) {
+        f3 r = cross(s, e1);
+        float v = f * dot(wd, r);
+        if (!(v < 0.0f || u + v > 1.0f)) {
           float t = f * dot(e2, r);
-          if (t < t_min || t > t_max) continue;
-          uint32_t id = fbits(a2.y);
-          if (better(t, cur_obj, id, best)) {
-            best.t = t; best.u = u; best.v = v; best.obj = cur_obj; best.prim = id;
-          }
-        }
-      } else {
-        // TLAS leaf: one top-level object
-        int obj = (int)first;
-        uint32_t q = (uint32_t)obj * RT_OBJ_QUADS;
-        float4 h = ldq(sc.objects, q);
-        int kind = (int)fbits(h.x);
-        if (kind == RT_OBJ_MESH) {
-          float4 r0 = ldq(sc.objects, q + 1), r1 = ldq(sc.objects, q + 2), r2 = ldq(sc.objects, q + 3);
-          float4 m7 = ldq(sc.objects, q + 7);
-          if (COUNT) cnt.inst += 1;
-          // StaticMesh::intersect_ray, geometry.rs:304: transform_point / transform_vector
-          f3 no = mk(r0.x * wo.x + r0.y * wo.y + r0.z * wo.z + r0.w * 1.0f,
-                     r1.x * wo.x + r1.y * wo.y + r1.z * wo.z + r1.w * 1.0f,
-                     r2.x * wo.x + r2.y * wo.y + r2.z * wo.z + r2.w * 1.0f);
-          f3 nd = mk(r0.x * wd.x + r0.y * wd.y + r0.z * wd.z + r0.w * 0.0f,
-                     r1.x * wd.x + r1.y * wd.y + r1.z * wd.z + r1.w * 0.0f,
-                     r2.x * wd.x + r2.y * wd.y + r2.z * wd.z + r2.w * 0.0f);
-          uint32_t root = fbits(m7.x);
-          if (root != RT_ENTRY_NONE) {
-            RT_PUSH(RT_ENTRY_RESTORE);
-            o = no; d = nd;
-            inv = approx_inv(d);
-            oi = mk(-o.x * inv.x, -o.y * inv.y, -o.z * inv.z);
-            in_blas = true;
-            cur_obj = obj;
-            entry = root;
-          }
-        } else {
-          if (COUNT) cnt.prims += 1;
-          float4 q1 = ldq(sc.objects, q + 1);
-          if (kind == RT_OBJ_SPHERE) {
-            float t;
-            if (sphere_t(mk(q1.x, q1.y, q1.z), q1.w, wo, wd, t_min, t_max, t) && better(t, obj, 0u, best)) {
-              best.t = t; best.obj = obj; best.prim = 0;
-            }
-          } else if (kind == RT_OBJ_TRIANGLE) {
-            // Triangle::intersect_ray, geometry.rs:433-447
-            float4 q2 = ldq(sc.objects, q + 2), q3 = ldq(sc.objects, q + 3);
-            f3 va = mk(q1.x, q1.y, q1.z), e1 = mk(q1.w, q2.x, q2.y), e2 = mk(q2.z, q2.w, q3.x);
-            f3 qv = cross(wd, e2);
-            float g = dot(e1, qv);
-            if (!(fabsf(g) < 0.0001f)) {
-              float f = 1.0f / g;
-              f3 s = wo - va;
-              float u = f * dot(s, qv);
-              if (!(u < 0.0f)) {
-                f3 r = cross(s, e1);
-                float v = f * dot(wd, r);
-                if (!(v < 0.0f || u + v > 1.0f)) {
-                  float t = f * dot(e2, r);
-                  if (!(t < t_min || t > t_max) && better(t, obj, 0u, best)) {
-                    best.t = t; best.obj = obj; best.prim = 0;
-                  }
-                }
-              }
-            }
-          } else if (kind == RT_OBJ_VOLUME) {
-            // ConvexVolume::intersect_ray with a Sphere boundary, geometry.rs:505-525
-            float4 q2 = ldq(sc.objects, q + 2);
-            f3 c = mk(q1.x, q1.y, q1.z);
-            float t_entr, t_exit;
-            if (sphere_t(c, q1.w, wo, wd, -CUDART_MAX_NORMAL_F, CUDART_MAX_NORMAL_F, t_entr) &&
-                sphere_t(c, q1.w, wo, wd, t_entr + 0.0001f, CUDART_MAX_NORMAL_F, t_exit) &&
-                !(t_exit < t_min || t_entr > t_max)) {
-              float t_start = fmaxf(t_entr, t_min);
-              float t_end = fminf(t_exit, t_max);
-              float dist_in = t_end - t_start;
-              uint32_t vi = fbits(q2.y);
-              u4 rr = philox4x32_10(pixel, sample, bounce, 1u + (vi >> 2), k0, k1);
-              uint32_t w = (vi & 3u) == 0 ? rr.x : ((vi & 3u) == 1 ? rr.y : ((vi & 3u) == 2 ? rr.z : rr.w));
-              float dist_before = (-1.0f / q2.x) * logf(u01(w));
-              if (dist_before < dist_in) {
-                float t = t_start + dist_before;
-                if (better(t, obj, 0u, best)) {
-                  best.t = t; best.obj = obj; best.prim = 0;
-                }
-              }
-            }
+          if (!(t < t_min || t > t_max) && better(t, obj, 0u, best)) {
+            best.t = t; best.obj = obj; best.prim = 0;
           }
         }
       }
     }
-    if (entry == RT_ENTRY_NONE) {
-      if (sp == 0) break;
-      RT_POP(entry);
-      if (entry == RT_ENTRY_RESTORE) {
-        o = wo; d = wd;
-        inv = approx_inv(d);
-        oi = mk(-o.x * inv.x, -o.y * inv.y, -o.z * inv.z);
-        in_blas = false;
-        entry = RT_ENTRY_NONE;
-        // fall through to pop the next entry on the next trip round the loop
-        if (sp == 0) break;
-        RT_POP(entry);
-        // a RESTORE marker is never directly below another one
+  } else if (kind == RT_OBJ_VOLUME) {
+    // ConvexVolume::intersect_ray with a Sphere boundary, geometry.rs:505-525
+    float4 q2 = ldq(sc.objects, q + 2);
+    f3 c = mk(q1.x, q1.y, q1.z);
+    float t_entr, t_exit;
+    if (sphere_t(c, q1.w, wo, wd, -CUDART_MAX_NORMAL_F, CUDART_MAX_NORMAL_F, t_entr) &&
+        sphere_t(c, q1.w, wo, wd, t_entr + 0.0001f, CUDART_MAX_NORMAL_F, t_exit) && !(t_exit < t_min || t_entr > t_max)) {
+      float t_start = fmaxf(t_entr, t_min);
+      float t_end = fminf(t_exit, t_max);
+      float dist_in = t_end - t_start;
+      uint32_t vi = fbits(q2.y);
+      float4 kc = T.qC[T.slot];
+      uint32_t pixel = fbits(kc.y), sb = fbits(kc.z);
+      u4 rr = philox4x32_10(pixel, sb & 0xFFFFFFu, sb >> 24, 1u + (vi >> 2), T.k0, T.k1);
+      uint32_t w = (vi & 3u) == 0 ? rr.x : ((vi & 3u) == 1 ? rr.y : ((vi & 3u) == 2 ? rr.z : rr.w));
+      float dist_before = (-1.0f / q2.x) * logf(u01(w));
+      if (dist_before < dist_in) {
+        float t = t_start + dist_before;
+        if (better(t, obj, 0u, best)) {
+          best.t = t; best.obj = obj; best.prim = 0;
+        }
       }
     }
   }
-#undef RT_PUSH
-#undef RT_POP
+}
 
-  // unbounded objects (planes) and anything the TLAS could not bound: always tested
+// unbounded objects (planes) and anything the TLAS could not bound: always tested
+template <bool COUNT>
+__device__ __forceinline__ void test_unbounded(const rt_dev_scene& sc, Trav& T, f3 wo, f3 wd) {
   const int32_t* planes = reinterpret_cast<const int32_t*>(sc.planes);
+  Best& best = T.best;
   for (uint32_t pi = 0; pi < sc.n_planes; ++pi) {
     int obj = __ldg(planes + pi);
     uint32_t q = (uint32_t)obj * RT_OBJ_QUADS;
     float4 h = ldq(sc.objects, q);
     int kind = (int)fbits(h.x);
     float4 q1 = ldq(sc.objects, q + 1), q2 = ldq(sc.objects, q + 2);
-    if (COUNT) cnt.prims += 1;
+    if (COUNT) T.cnt.prims += 1;
     if (kind == RT_OBJ_PLANE) {
       // Plane::intersect_ray, geometry.rs:476-485
       f3 nrm = mk(q2.x, q2.y, q2.z);
@@ -400,12 +413,50 @@ __device__ __forceinline__ void closest_hit(const rt_dev_scene& sc, f3 wo, f3 wd
       float dd = dot(wd, n);
       if (!(dd >= 0.0f)) {
         float t = fabsf(od) / fabsf(dd);
-        if (!(t < t_min || t > t_max) && better(t, obj, 0u, best)) {
+        if (!(t < T.t_min || t > T.t_max) && better(t, obj, 0u, best)) {
           best.t = t; best.obj = obj; best.prim = 0;
         }
       }
     }
   }
+}
+
+// start the closest-hit query of the ray in T.wo / T.wd
+template <bool COUNT>
+__device__ __forceinline__ void test_unbounded(const rt_dev_scene& sc, Trav& T, f3 wo, f3 wd);
+
+template <bool COUNT>
+__device__ __forceinline__ void trav_begin(const rt_dev_scene& sc, Trav& T, f3 wo, f3 wd) {
+  T.set_space(wo, wd);
+  T.best.t = T.t_max;
+  T.best.obj = -1;
+  T.best.prim = 0;
+  T.best.u = T.best.v = 0.0f;
+  T.cnt = Cnt{0, 0, 0, 0, 0};
+  T.sp = 0;
+  T.in_blas = false;
+  T.cur_obj = -1;
+  // unbounded objects first: a plane hit (the floor is the most common hit of all) shortens the
+  // interval before any node is fetched.  Candidate ordering is order independent (see better()).
+  test_unbounded<COUNT>(sc, T, wo, wd);
+  T.entry = sc.tlas_root;
+  if (T.entry != RT_ENTRY_NONE) {
+    float tn;
+    float4 lo = make_float4(sc.tlas_min[0], sc.tlas_min[1], sc.tlas_min[2], 0.0f);
+    float4 hi = make_float4(sc.tlas_max[0], sc.tlas_max[1], sc.tlas_max[2], 0.0f);
+    if (!slab(lo, hi, T.inv, T.oi, T.t_min, T.best.t, tn)) T.entry = RT_ENTRY_NONE;
+  }
+}
+// one round: descend while interior, then the leaf this lane reached (if any), then pop.
+// Returns true when the stack is exhausted.  (Measured on B200: postponing leaves until every lane
+// of the warp holds one - "while-while" - is 30 % slower here, because leaves are cheap (1.9
+// triangle tests per ray) compared with the descent they would make the other lanes wait for.)
+template <bool COUNT>
+__device__ __forceinline__ bool trav_round(const rt_dev_scene& sc, Trav& T) {
+  if (COUNT) T.cnt.rounds += 1;
+  while (T.entry != RT_ENTRY_NONE && !(T.entry & RT_LEAF_FLAG)) trav_interior<COUNT>(sc, T);
+  if (T.entry != RT_ENTRY_NONE) trav_leaf<COUNT>(sc, T);
+  return T.entry == RT_ENTRY_NONE && !T.pop_next();
 }
 
 // nearest RGB8 tap, texture.rs:28-31 (Q7)
@@ -516,89 +567,153 @@ __global__ void k_advance(rt_ctrl* c, uint32_t capacity) {
   c->work_base = c->cursor;
   c->cursor += n_new;
   c->n_next = 0;
+  c->next_ray = 0;
 #pragma unroll
   for (int i = 0; i < RT_NUM_CLASSES; ++i) c->class_count[i] = 0;
   if (n_cont + n_new == 0) c->done = 1;
   else c->iterations += 1;
 }
 
-// ------------------------------------------------------------------ k_extend
-template <bool COUNT, bool DEBUG>
-__global__ void __launch_bounds__(RT_BLOCK) k_extend(rt_dev_scene sc, rt_frame fr, rt_ctrl* __restrict__ ctrl,
-                                                     rt_paths cur, rt_hits hits, uint32_t* __restrict__ queues,
-                                                     rt_debug dbg) {
+// ------------------------------------------------------------------ k_raygen
+// camera rays for the paths started this iteration: slots [n_cont, n_rays) of the ray queue
+__global__ void __launch_bounds__(RT_BLOCK) k_raygen(rt_frame fr, rt_ctrl* __restrict__ ctrl, rt_paths cur) {
+  const uint32_t n_rays = ctrl->n_rays, n_cont = ctrl->n_cont;
+  const uint32_t k = blockIdx.x * RT_BLOCK + threadIdx.x;
+  if (k >= n_rays - n_cont) return;
+  const uint32_t i = n_cont + k;
+  uint32_t x, y, sample;
+  if (work_to_pixel(fr, ctrl->work_base + k, x, y, sample)) {
+    uint32_t pixel = y * fr.width + x;
+    f3 o, d;
+    camera_ray(fr, x, y, pixel, sample, o, d);
+    cur.A[i] = make_float4(o.x, o.y, o.z, d.x);
+    cur.B[i] = make_float4(d.y, d.z, 1.0f, 1.0f);
+    cur.C[i] = make_float4(1.0f, __uint_as_float(pixel), __uint_as_float(sample), 0.0f);  // bounce 0
+  } else {
+    // tile slot outside the image: a direction of all zeros marks "no ray" for k_trace
+    atomicAdd(&ctrl->counters[7], 1ull);
+    cur.A[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    cur.B[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    cur.C[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+}
+
+// ------------------------------------------------------------------ k_trace
+// Persistent warps that claim ray indices in chunks (one atomic per RT_FETCH_CHUNK rays) and do
+// nothing but traverse: fetching a ray is two 128-bit loads, retiring one is a 20-byte store.
+// A warp can refill idle lanes before the whole batch is done (RT_REFILL_MIN idle lanes trigger a
+// refill).  Measured on C4 / B200 (profiles/r1_notes.md): although only 21 % of the lanes of a
+// batch are busy in node-visit terms, refilling early is SLOWER (R=4: 535 us, R=8: 509, R=16: 496,
+// R=32: 477 per iteration) - a fresh batch of 32 camera rays of one pixel traverses in lockstep,
+// and mixing in rays from elsewhere destroys that; the idle tail of a batch is cheap because the
+// few lanes left no longer wait for each other.  Hence the default of 32 = refill only when the
+// whole warp is idle.
+#ifndef RT_REFILL_MIN
+#define RT_REFILL_MIN 32
+#endif
+#ifndef RT_FETCH_CHUNK
+#define RT_FETCH_CHUNK 64
+#endif
+
+template <bool COUNT>
+__global__ void __launch_bounds__(RT_BLOCK, RT_EXTEND_MIN_BLOCKS) k_trace(rt_dev_scene sc, rt_frame fr, rt_ctrl* __restrict__ ctrl,
+                                                                        rt_paths cur, rt_hits hits) {
   __shared__ uint32_t sstack[RT_SMEM_STACK * RT_BLOCK];
+  const uint32_t n_rays = ctrl->n_rays;
+  const uint32_t lane = threadIdx.x & 31u;
+  const uint32_t FULL = 0xFFFFFFFFu;
+  uint32_t lstack[RT_LOCAL_STACK];
+  Trav T;
+  T.sstack = sstack;
+  T.lstack = lstack;
+  T.t_min = fr.t_min; T.t_max = fr.t_max;
+  T.k0 = fr.k0; T.k1 = fr.k1;
+  T.qA = cur.A; T.qB = cur.B; T.qC = cur.C;
+  T.slot = 0;
+  bool have = false, fin = false;
+  uint32_t c_next = 0, c_end = 0;  // this warp's claimed chunk of ray indices (warp uniform)
+  bool exhausted = false;          // the queue has no more chunks (warp uniform)
+
+  for (;;) {
+    // ---- retire finished lanes: the compact hit record is all k_shade needs to redo the rest
+    if (have && fin) {
+      const Best& best = T.best;
+      hits.H[T.slot] = make_float4(best.t, best.u, best.v, __uint_as_float(best.prim));
+      hits.obj[T.slot] = best.obj;
+      if (COUNT) {
+        atomicAdd(&ctrl->counters[0], (unsigned long long)T.cnt.nodes);
+        atomicAdd(&ctrl->counters[1], (unsigned long long)T.cnt.tris);
+        atomicAdd(&ctrl->counters[2], (unsigned long long)T.cnt.inst);
+        atomicAdd(&ctrl->counters[3], (unsigned long long)T.cnt.prims);
+      }
+      have = false;
+      fin = false;
+    }
+    // ---- refill idle lanes
+    uint32_t need = __ballot_sync(FULL, !have);
+    if ((need == FULL || __popc(need) >= RT_REFILL_MIN) && !(exhausted && c_next >= c_end)) {
+      uint32_t n_need = __popc(need);
+      if (c_next >= c_end && !exhausted) {
+        uint32_t base = 0;
+        if (lane == 0) base = atomicAdd(&ctrl->next_ray, (uint32_t)RT_FETCH_CHUNK);
+        base = __shfl_sync(FULL, base, 0);
+        c_next = base;
+        c_end = min(base + (uint32_t)RT_FETCH_CHUNK, n_rays);
+        if (base + RT_FETCH_CHUNK >= n_rays) exhausted = true;
+        if (base >= n_rays) c_end = c_next = 0;
+      }
+      uint32_t my = c_next + __popc(need & ((1u << lane) - 1u));
+      if (!have && my < c_end) {
+        float4 a = cur.A[my], b = cur.B[my];
+        f3 wo = mk(a.x, a.y, a.z), wd = mk(a.w, b.x, b.y);
+        if (wd.x == 0.0f && wd.y == 0.0f && wd.z == 0.0f && b.z == 0.0f) {
+          hits.obj[my] = -1;  // "no ray" marker written by k_raygen
+        } else {
+          T.slot = my;
+          trav_begin<COUNT>(sc, T, wo, wd);
+          have = true;
+          fin = false;
+        }
+      }
+      c_next = min(c_next + n_need, c_end);
+    }
+    uint32_t busy = __ballot_sync(FULL, have);
+    if (busy == 0) {
+      if (exhausted && c_next >= c_end) break;
+      continue;
+    }
+    // ---- traverse until enough lanes are idle again (or nothing is left to fetch)
+    const bool can_refill = !(exhausted && c_next >= c_end);
+    for (;;) {
+      if (have && !fin) fin = trav_round<COUNT>(sc, T);
+      uint32_t run = __ballot_sync(FULL, have && !fin);
+      if (run == 0) break;
+      if (can_refill && 32 - __popc(run) >= RT_REFILL_MIN) break;
+    }
+  }
+}
+
+// ------------------------------------------------------------------ k_sort
+// material-sorted shade queues: warp match groups -> per-warp counts -> one atomic per class per
+// block -> each hit ray's slot index lands in the queue of its material class
+__global__ void __launch_bounds__(RT_BLOCK) k_sort(rt_dev_scene sc, rt_frame fr, rt_ctrl* __restrict__ ctrl,
+                                                   const int32_t* __restrict__ hit_obj, uint32_t* __restrict__ queues) {
   __shared__ uint32_t s_wcount[RT_WARPS][RT_NUM_CLASSES];
   __shared__ uint32_t s_base[RT_NUM_CLASSES];
-  const uint32_t n_rays = ctrl->n_rays, n_cont = ctrl->n_cont;
+  const uint32_t n_rays = ctrl->n_rays;
   const uint32_t i = blockIdx.x * RT_BLOCK + threadIdx.x;
-  if (blockIdx.x * RT_BLOCK >= n_rays) return;  // whole block idle
+  if (blockIdx.x * RT_BLOCK >= n_rays) return;
   const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-
   int cls = -1;
   if (i < n_rays) {
-    f3 o, d;
-    uint32_t pixel, sb;
-    bool valid = true;
-    if (i < n_cont) {
-      float4 a = cur.A[i], b = cur.B[i];
-      float4 c = cur.C[i];
-      o = mk(a.x, a.y, a.z);
-      d = mk(a.w, b.x, b.y);
-      pixel = fbits(c.y);
-      sb = fbits(c.z);
-    } else {
-      uint32_t x, y, sample;
-      valid = work_to_pixel(fr, ctrl->work_base + (i - n_cont), x, y, sample);
-      pixel = y * fr.width + x;
-      sb = sample;  // bounce 0 in the top byte
-      if (!valid) atomicAdd(&ctrl->counters[7], 1ull);  // tile slot outside the image
-      if (valid) {
-        camera_ray(fr, x, y, pixel, sample, o, d);
-        cur.A[i] = make_float4(o.x, o.y, o.z, d.x);
-        cur.B[i] = make_float4(d.y, d.z, 1.0f, 1.0f);
-        cur.C[i] = make_float4(1.0f, __uint_as_float(pixel), __uint_as_float(sb), 0.0f);
-      }
-    }
-    if (valid) {
-      Best best;
-      Cnt cnt = {0, 0, 0, 0};
-      closest_hit<COUNT>(sc, o, d, fr.t_min, fr.t_max, fr.k0, fr.k1, pixel, sb & 0xFFFFFFu, sb >> 24, sstack, best, cnt);
-      if (COUNT) {
-        atomicAdd(&ctrl->counters[0], (unsigned long long)cnt.nodes);
-        atomicAdd(&ctrl->counters[1], (unsigned long long)cnt.tris);
-        atomicAdd(&ctrl->counters[2], (unsigned long long)cnt.inst);
-        atomicAdd(&ctrl->counters[3], (unsigned long long)cnt.prims);
-      }
-      if (DEBUG) {
-        if (dbg.obj) dbg.obj[i] = best.obj;
-        if (dbg.prim) dbg.prim[i] = best.obj >= 0 ? (int)best.prim : 0;
-        if (dbg.t) dbg.t[i] = best.obj >= 0 ? best.t : 0.0f;
-      }
-      if (best.obj >= 0) {
-        Surface s;
-        resolve_hit<COUNT>(sc, o, d, best, s, ctrl->counters);
-        hits.H0[i] = make_float4(s.hp.x, s.hp.y, s.hp.z, s.n.x);
-        hits.H1[i] = make_float4(s.n.y, s.n.z, s.u, s.v);
-        hits.H2[i] = s.meta;
-        cls = (int)(s.meta & 7u);
-      } else if (DEBUG) {
-        hits.H0[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-        hits.H1[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-        hits.H2[i] = 0xFFFFFFFFu;
-      }
-    }
+    int obj = hit_obj[i];
+    if (obj >= 0) cls = (int)fbits(ldq(sc.objects, (uint32_t)obj * RT_OBJ_QUADS).z);
   }
-
-  // material-sorted enqueue: warp match groups -> per-warp counts -> one atomic per class per block
   if (threadIdx.x < RT_WARPS * RT_NUM_CLASSES) (&s_wcount[0][0])[threadIdx.x] = 0;
   __syncthreads();
-  uint32_t rank = 0;
-  {
-    uint32_t peers = __match_any_sync(0xFFFFFFFFu, cls);
-    rank = __popc(peers & ((1u << lane) - 1u));
-    if (cls >= 0 && rank == 0) s_wcount[warp][cls] = __popc(peers);
-  }
+  uint32_t peers = __match_any_sync(0xFFFFFFFFu, cls);
+  uint32_t rank = __popc(peers & ((1u << lane) - 1u));
+  if (cls >= 0 && rank == 0) s_wcount[warp][cls] = __popc(peers);
   __syncthreads();
   if (threadIdx.x < RT_NUM_CLASSES) {
     uint32_t total = 0;
@@ -612,6 +727,28 @@ __global__ void __launch_bounds__(RT_BLOCK) k_extend(rt_dev_scene sc, rt_frame f
   }
   __syncthreads();
   if (cls >= 0) queues[(size_t)cls * fr.capacity + s_base[cls] + s_wcount[warp][cls] + rank] = i;
+}
+
+// ------------------------------------------------------------------ k_surface (parity hooks only)
+__global__ void __launch_bounds__(RT_BLOCK) k_surface(rt_dev_scene sc, rt_ctrl* __restrict__ ctrl, rt_paths cur, rt_hits hits,
+                                                      rt_debug dbg) {
+  const uint32_t i = blockIdx.x * RT_BLOCK + threadIdx.x;
+  if (i >= ctrl->n_rays) return;
+  float4 h = hits.H[i];
+  Best b;
+  b.t = h.x; b.u = h.y; b.v = h.z; b.prim = fbits(h.w);
+  b.obj = hits.obj[i];
+  Surface s;
+  s.hp = s.n = mk(0.f, 0.f, 0.f);
+  s.u = s.v = 0.0f;
+  s.meta = 0xFFFFFFFFu;
+  if (b.obj >= 0) {
+    float4 a = cur.A[i], bq = cur.B[i];
+    resolve_hit<false>(sc, mk(a.x, a.y, a.z), mk(a.w, bq.x, bq.y), b, s, ctrl->counters);
+  }
+  dbg.S0[i] = make_float4(s.hp.x, s.hp.y, s.hp.z, s.n.x);
+  dbg.S1[i] = make_float4(s.n.y, s.n.z, s.u, s.v);
+  dbg.S2[i] = s.meta;
 }
 
 // ------------------------------------------------------------------ materials
@@ -709,14 +846,22 @@ __global__ void __launch_bounds__(RT_BLOCK) k_shade(rt_dev_scene sc, rt_frame fr
   if (j < count) {
     uint32_t slot = queues[(size_t)cls * fr.capacity + j];
     float4 a = cur.A[slot], bq = cur.B[slot], c = cur.C[slot];
-    float4 h0 = hits.H0[slot], h1 = hits.H1[slot];
-    uint32_t meta = hits.H2[slot];
+    f3 o = mk(a.x, a.y, a.z);
     f3 d = mk(a.w, bq.x, bq.y);
     f3 T = mk(bq.z, bq.w, c.x);
     pixel = fbits(c.y);
     sb = fbits(c.z);
     uint32_t sample = sb & 0xFFFFFFu, bounce = sb >> 24;
-    f3 hp = mk(h0.x, h0.y, h0.z), n = mk(h0.w, h1.x, h1.y);
+    // hit resolution: what the reference attaches to its RayHit
+    float4 hr = hits.H[slot];
+    Best best;
+    best.t = hr.x; best.u = hr.y; best.v = hr.z; best.prim = fbits(hr.w);
+    best.obj = hits.obj[slot];
+    Surface sf;
+    resolve_hit<COUNT>(sc, o, d, best, sf, ctrl->counters);
+    f3 hp = sf.hp, n = sf.n;
+    float4 h1 = make_float4(0.f, 0.f, sf.u, sf.v);
+    uint32_t meta = sf.meta;
     bool front = (meta >> 3) & 1u;
     uint32_t id = meta >> 4;
 
@@ -873,6 +1018,7 @@ __global__ void k_init_ctrl(rt_ctrl* c, unsigned long long total) {
   c->n_rays = 0;
   c->work_base = 0;
   c->n_next = 0;
+  c->next_ray = 0;
   for (int i = 0; i < RT_NUM_CLASSES; ++i) c->class_count[i] = 0;
   c->done = 0;
   c->iterations = 0;
@@ -890,16 +1036,24 @@ void launch_advance(rt_ctrl* ctrl, uint32_t capacity, cudaStream_t st) {
   k_advance<<<1, 1, 0, st>>>(ctrl, capacity);
   k_tally<<<1, 1, 0, st>>>(ctrl);
 }
+int trace_blocks_per_sm() {
+  int n = 0;
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_trace<false>, RT_BLOCK, 0);
+  return n > 0 ? n : 1;
+}
+// ray-gen for the new paths, closest hit for every ray, material-sorted queues
 void launch_extend(const rt_dev_scene& sc, const rt_frame& fr, rt_ctrl* ctrl, rt_paths cur, rt_hits hits,
-                   uint32_t* queues, rt_debug dbg, bool count, bool debug, cudaStream_t st) {
-  uint32_t grid = (fr.capacity + RT_BLOCK - 1) / RT_BLOCK;
-  if (debug) {
-    if (count) k_extend<true, true><<<grid, RT_BLOCK, 0, st>>>(sc, fr, ctrl, cur, hits, queues, dbg);
-    else k_extend<false, true><<<grid, RT_BLOCK, 0, st>>>(sc, fr, ctrl, cur, hits, queues, dbg);
-  } else {
-    if (count) k_extend<true, false><<<grid, RT_BLOCK, 0, st>>>(sc, fr, ctrl, cur, hits, queues, dbg);
-    else k_extend<false, false><<<grid, RT_BLOCK, 0, st>>>(sc, fr, ctrl, cur, hits, queues, dbg);
-  }
+                   uint32_t* queues, bool count, bool have_new_rays, uint32_t persistent_blocks, cudaStream_t st) {
+  uint32_t full = (fr.capacity + RT_BLOCK - 1) / RT_BLOCK;
+  if (have_new_rays) k_raygen<<<full, RT_BLOCK, 0, st>>>(fr, ctrl, cur);
+  uint32_t grid = full < persistent_blocks ? full : persistent_blocks;  // never more blocks than there could be rays
+  if (count) k_trace<true><<<grid, RT_BLOCK, 0, st>>>(sc, fr, ctrl, cur, hits);
+  else k_trace<false><<<grid, RT_BLOCK, 0, st>>>(sc, fr, ctrl, cur, hits);
+  k_sort<<<full, RT_BLOCK, 0, st>>>(sc, fr, ctrl, hits.obj, queues);
+}
+void launch_surface(const rt_dev_scene& sc, const rt_frame& fr, rt_ctrl* ctrl, rt_paths cur, rt_hits hits, rt_debug dbg,
+                    cudaStream_t st) {
+  k_surface<<<(fr.capacity + RT_BLOCK - 1) / RT_BLOCK, RT_BLOCK, 0, st>>>(sc, ctrl, cur, hits, dbg);
 }
 void launch_shade(const rt_dev_scene& sc, const rt_frame& fr, rt_ctrl* ctrl, rt_paths cur, rt_paths nxt, rt_hits hits,
                   const uint32_t* queues, long long* accum, bool count, cudaStream_t st) {

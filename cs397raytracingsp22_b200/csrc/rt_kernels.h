@@ -16,23 +16,25 @@ struct rt_paths {
   float4* B;
   float4* C;
 };
-// hit records written by k_extend for k_shade (36 B per ray): H0=(hitpoint.xyz,n.x) H1=(n.yz,u,v) H2=meta
+// hit records written by k_trace for k_sort / k_shade (20 B per ray): H=(t,u,v,triangle id) obj=object or -1
 struct rt_hits {
-  float4* H0;
-  float4* H1;
-  uint32_t* H2;
-};
-// parity hooks only
-struct rt_debug {
+  float4* H;
   int32_t* obj;
-  int32_t* prim;
-  float* t;
+};
+// parity hooks only: resolved surface per ray: S0=(hitpoint.xyz,n.x) S1=(n.yz,u,v) S2=class|frontface<<3|id<<4
+struct rt_debug {
+  float4* S0;
+  float4* S1;
+  uint32_t* S2;
 };
 
 void launch_init(rt_ctrl* ctrl, unsigned long long total, cudaStream_t st);
 void launch_advance(rt_ctrl* ctrl, uint32_t capacity, cudaStream_t st);
 void launch_extend(const rt_dev_scene& sc, const rt_frame& fr, rt_ctrl* ctrl, rt_paths cur, rt_hits hits,
-                   uint32_t* queues, rt_debug dbg, bool count, bool debug, cudaStream_t st);
+                   uint32_t* queues, bool count, bool have_new_rays, uint32_t persistent_blocks, cudaStream_t st);
+void launch_surface(const rt_dev_scene& sc, const rt_frame& fr, rt_ctrl* ctrl, rt_paths cur, rt_hits hits, rt_debug dbg,
+                    cudaStream_t st);
+int trace_blocks_per_sm();
 void launch_shade(const rt_dev_scene& sc, const rt_frame& fr, rt_ctrl* ctrl, rt_paths cur, rt_paths nxt, rt_hits hits,
                   const uint32_t* queues, long long* accum, bool count, cudaStream_t st);
 void launch_resolve(const long long* accum, uint32_t npix, uint32_t spp, float gamma, float* out_linear,

@@ -83,6 +83,17 @@ inline float half_area(const float* mn, const float* mx) {
   return ex * ey + ey * ez + ez * ex;
 }
 
+// tuning knobs (development): RT_LEAF_MAX (1..8), RT_SAH_CT (cost of a node-pair visit in triangle tests)
+float g_sah_ct = 1.0f;
+uint32_t g_leaf_max = 4;
+void read_knobs() {
+  static bool done = false;
+  if (done) return;
+  done = true;
+  if (const char* e = std::getenv("RT_LEAF_MAX")) g_leaf_max = (uint32_t)std::min(RT_MAX_LEAF_TRIS, std::max(1, std::atoi(e)));
+  if (const char* e = std::getenv("RT_SAH_CT")) g_sah_ct = (float)std::atof(e);
+}
+
 void subdivide(std::vector<BPrim>& prims, std::vector<BNode>& nodes, uint32_t ni, uint32_t max_leaf) {
   const int NB = 16;
   uint32_t first = nodes[ni].leftFirst, count = nodes[ni].count;
@@ -168,8 +179,8 @@ void subdivide(std::vector<BPrim>& prims, std::vector<BNode>& nodes, uint32_t ni
 
   float parent_area = half_area(mn, mx);
   bool must_split = count > max_leaf;
-  // cost model: one node-pair visit ~ one triangle test
-  bool sah_split = best_axis >= 0 && (best_cost + parent_area) < parent_area * (float)count;
+  // cost model: one node-pair visit costs g_sah_ct triangle tests
+  bool sah_split = best_axis >= 0 && (best_cost + g_sah_ct * parent_area) < parent_area * (float)count;
   if (!must_split && !sah_split) return;
 
   uint32_t mid;
@@ -280,7 +291,8 @@ void build_mesh(HostMesh& m) {
   m.n_reachable = (uint32_t)prims.size();
 
   std::vector<BNode> nodes;
-  build_bvh(prims, 4, nodes);
+  read_knobs();
+  build_bvh(prims, g_leaf_max, nodes);
   // Conservative traversal: boxes are padded by a few ulps of the largest coordinate so that a
   // triangle the reference's Möller–Trumbore test accepts is never culled by rounding in the
   // slab test (flat boxes of coplanar triangles get thickness this way, cf. Q3).
@@ -546,6 +558,9 @@ int lower_scene(const std::vector<HostTexture>& textures, const std::vector<rt_m
     }
   }
   if (L.nodes.empty()) L.nodes.assign(RT_NODE_QUADS * 2, Quad{});
+  // final form of the link word: the packed traversal entry (leaf flag | first << 4 | count, or the
+  // index of the child pair), so the kernel uses lo.w as is; hi.w keeps the plain count
+  for (size_t q = 0; q < L.nodes.size(); q += 2) L.nodes[q].u[3] = pack_entry(L.nodes[q].u[3], L.nodes[q + 1].u[3]);
   return RT_OK;
 }
 

@@ -3,10 +3,12 @@
 // each record is fetched with 128-bit read-only loads.
 //
 // Lowered scene, all in HBM (and in practice L2-resident):
-//   nodes   : 2 quads (32 B) per BVH node  lo=(min.xyz, leftFirst) hi=(max.xyz, count)
-//             count==0: interior, children are nodes leftFirst and leftFirst+1 (one 64 B pair)
-//             count>0 : leaf; BLAS leaf => `count` triangle records from `leftFirst`,
-//                             TLAS leaf => count==1, leftFirst = top-level object index
+//   nodes   : 2 quads (32 B) per BVH node  lo=(min.xyz, link) hi=(max.xyz, count)
+//             count==0: interior, link = index of the left child; children are nodes link and link+1
+//                       (one 64-byte pair, fetched together)
+//             count>0 : leaf, link = RT_LEAF_FLAG | first << 4 | count;
+//                       BLAS leaf => `count` triangle records from `first`,
+//                       TLAS leaf => count==1, first = top-level object index
 //   tris    : 3 quads (48 B) per triangle, leaf order: (v0.xyz,e1.x)(e1.yz,e2.xy)(e2.z,id,_,_)
 //   shade   : 5 quads (80 B) per triangle, ORIGINAL order: na nb nc uva uvb uvc tangent
 //   objects : 10 quads (160 B) per top-level object, insertion order (tie-breaking!)
@@ -70,6 +72,8 @@ struct rt_ctrl {
   uint32_t n_rays;                 // rays this iteration (n_cont + newly generated)
   unsigned long long work_base;    // work index of the first newly generated ray
   uint32_t n_next;                 // shade's output counter (next iteration's n_cont)
+  uint32_t next_ray;               // k_extend's dynamic ray fetch cursor
+  uint32_t pad0_;
   uint32_t class_count[RT_NUM_CLASSES];
   uint32_t done;                   // 1 when cursor==total and nothing is in flight
   uint32_t iterations;

@@ -122,6 +122,8 @@ typedef struct rt_stats {
   uint64_t texel_taps;        /* RGB8 texel fetches (all kernels)                   */
   uint64_t extend_texel_taps; /* of those, normal-map taps made inside k_extend     */
   uint64_t material_fetches;  /* 32-byte material records fetched                   */
+  uint64_t warp_node_slots;   /* 32 x (most nodes fetched by any lane) summed over warp batches:
+                                 nodes_visited / warp_node_slots = SIMT efficiency of traversal */
   /* CUDA-event times on the render stream, milliseconds */
   double ms_total;
   double ms_extend;
