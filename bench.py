@@ -194,10 +194,10 @@ def extend_algorithmic_bytes(st) -> float:
     """Algorithmic bytes of ALL k_extend launches of one frame (DESIGN.md "roofline accounting"):
     32 B per BVH node fetched, 48 B per triangle record, 96 B of transforms per instance entered, 32 B per analytic
     primitive record, 80 B per mesh shading record, 4 B per normal-map tap, plus the wavefront's own ray traffic:
-    48 B ray read (or written, for a new camera ray) + 36 B hit record + 4 B queue entry per ray."""
+    48 B ray read (or written, for a new camera ray) + 20 B hit record + 4 B queue entry per ray."""
     return (32.0 * st["nodes_visited"] + 48.0 * st["tris_tested"] + 96.0 * st["instances_entered"]
             + 32.0 * st["prims_tested"] + 80.0 * st["mesh_hits"] + 4.0 * st["extend_texel_taps"]
-            + 88.0 * st["rays"])
+            + 72.0 * st["rays"])
 
 
 def main():
@@ -374,7 +374,7 @@ def main():
                                                   "Philox key; one NCCL int64 reduce per frame" if world > 1 and args.shard == "weak"
                                                   else ("single GPU" if world == 1 else f"one frame sharded by {args.shard}")),
             "total_spp": total_spp, "l2": "flush (256 MiB memset between timed iterations)",
-            "wavefront": int(args.wavefront or (1 << 21)), "scene_build_s": build_s,
+            "wavefront": int(args.wavefront or (1 << 23)), "scene_build_s": build_s,
             "scene_bytes": int(g.device_bytes()),
         }),
         "rays_per_sec_M": rays_M, "rays_per_sample": job_rays / max(job_samples, 1),

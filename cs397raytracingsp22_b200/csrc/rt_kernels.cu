@@ -27,9 +27,13 @@
 
 namespace rt {
 
+#ifndef RT_BLOCK
 #define RT_BLOCK 128
+#endif
 #define RT_WARPS (RT_BLOCK / 32)
+#ifndef RT_SMEM_STACK
 #define RT_SMEM_STACK 16   // traversal-stack entries per thread kept in shared memory
+#endif
 #define RT_LOCAL_STACK 48  // overflow entries (local memory; host checks depth <= 62)
 #ifndef RT_EXTEND_MIN_BLOCKS
 #define RT_EXTEND_MIN_BLOCKS 8  // 64 registers per thread -> 32 resident warps per SM
@@ -217,7 +221,7 @@ struct Trav {
   int sp;
   int cur_obj;
   bool in_blas;
-  uint32_t* sstack;
+  uint32_t sbase;    // shared-space byte address of this thread's stack column ([depth][thread] layout)
   uint32_t* lstack;  // RT_LOCAL_STACK entries of local memory, declared by the kernel
   Best best;
   Cnt cnt;
@@ -229,13 +233,16 @@ struct Trav {
   }
 
   __device__ __forceinline__ void push(uint32_t v) {
-    if (sp < RT_SMEM_STACK) sstack[sp * RT_BLOCK + threadIdx.x] = v;
+    if (sp < RT_SMEM_STACK) asm volatile("st.shared.u32 [%0], %1;" ::"r"(sbase + (uint32_t)sp * (RT_BLOCK * 4u)), "r"(v) : "memory");
     else lstack[sp - RT_SMEM_STACK] = v;
     ++sp;
   }
   __device__ __forceinline__ uint32_t pop() {
     --sp;
-    return sp < RT_SMEM_STACK ? sstack[sp * RT_BLOCK + threadIdx.x] : lstack[sp - RT_SMEM_STACK];
+    uint32_t v;
+    if (sp < RT_SMEM_STACK) asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(sbase + (uint32_t)sp * (RT_BLOCK * 4u)) : "memory");
+    else v = lstack[sp - RT_SMEM_STACK];
+    return v;
   }
   __device__ __forceinline__ void set_space(f3 no, f3 nd) {
     o = no; d = nd;
@@ -263,8 +270,8 @@ struct Trav {
 template <bool COUNT>
 __device__ __forceinline__ void trav_interior(const rt_dev_scene& sc, Trav& T) {
   uint32_t e = T.entry;
-  float4 l0 = ldq(sc.nodes, e * 2u), l1 = ldq(sc.nodes, e * 2u + 1u);
-  float4 r0 = ldq(sc.nodes, e * 2u + 2u), r1 = ldq(sc.nodes, e * 2u + 3u);
+  const float4* pair = reinterpret_cast<const float4*>(sc.nodes) + (size_t)e * 2u;
+  float4 l0 = __ldg(pair), l1 = __ldg(pair + 1), r0 = __ldg(pair + 2), r1 = __ldg(pair + 3);
   if (COUNT) T.cnt.nodes += 2;
   float tl, tr;
   bool hl = slab(l0, l1, T.inv, T.oi, T.t_min, T.best.t, tl);
@@ -612,7 +619,7 @@ __global__ void __launch_bounds__(RT_BLOCK) k_raygen(rt_frame fr, rt_ctrl* __res
 #define RT_REFILL_MIN 32
 #endif
 #ifndef RT_FETCH_CHUNK
-#define RT_FETCH_CHUNK 64
+#define RT_FETCH_CHUNK 32  // measured: 32 -> 436 us, 64 -> 477 us, 256 -> 703 us per 2 M-ray iteration (load balance)
 #endif
 
 template <bool COUNT>
@@ -624,7 +631,7 @@ __global__ void __launch_bounds__(RT_BLOCK, RT_EXTEND_MIN_BLOCKS) k_trace(rt_dev
   const uint32_t FULL = 0xFFFFFFFFu;
   uint32_t lstack[RT_LOCAL_STACK];
   Trav T;
-  T.sstack = sstack;
+  T.sbase = (uint32_t)__cvta_generic_to_shared(sstack) + threadIdx.x * 4u;
   T.lstack = lstack;
   T.t_min = fr.t_min; T.t_max = fr.t_max;
   T.k0 = fr.k0; T.k1 = fr.k1;
@@ -645,6 +652,11 @@ __global__ void __launch_bounds__(RT_BLOCK, RT_EXTEND_MIN_BLOCKS) k_trace(rt_dev
         atomicAdd(&ctrl->counters[1], (unsigned long long)T.cnt.tris);
         atomicAdd(&ctrl->counters[2], (unsigned long long)T.cnt.inst);
         atomicAdd(&ctrl->counters[3], (unsigned long long)T.cnt.prims);
+        // SIMT diagnostic (meaningful with RT_REFILL_MIN == 32, i.e. whole batches retire together): nodes fetched
+        // by the lanes of the batch vs 32 x what its slowest lane fetched
+        uint32_t m = __activemask();
+        uint32_t wmax = __reduce_max_sync(m, T.cnt.nodes);
+        if ((m & ((1u << lane) - 1u)) == 0) atomicAdd(&ctrl->counters[9], (unsigned long long)wmax * 32ull);
       }
       have = false;
       fin = false;
@@ -823,8 +835,15 @@ __global__ void __launch_bounds__(RT_BLOCK) k_shade(rt_dev_scene sc, rt_frame fr
   uint32_t b = blockIdx.x;
   int cls = -1;
   uint32_t count = 0;
+  // Blocks serve the classes in the order below, and survivors get their place in the next ray queue in block
+  // order.  Rays leaving a textured mesh start inside a BLAS and are the most expensive to trace, rays leaving
+  // analytic surfaces are cheap, new camera rays (appended behind all of these) are cheapest: longest first, so
+  // k_trace's tail is filled with short, coherent batches.
+  const int order[RT_NUM_CLASSES] = {RT_CLASS_PARAM_TEX, RT_CLASS_DIELECTRIC, RT_CLASS_METAL, RT_CLASS_LAMBERT,
+                                     RT_CLASS_ISOTROPIC, RT_CLASS_PARAM};
 #pragma unroll
-  for (int c = 0; c < RT_NUM_CLASSES; ++c) {
+  for (int k = 0; k < RT_NUM_CLASSES; ++k) {
+    const int c = order[k];
     uint32_t n = ctrl->class_count[c];
     uint32_t nb = (n + RT_BLOCK - 1) / RT_BLOCK;
     if (cls < 0) {
