@@ -35,6 +35,11 @@ namespace rt {
 #define RT_SMEM_STACK 16   // traversal-stack entries per thread kept in shared memory
 #endif
 #define RT_LOCAL_STACK 48  // overflow entries (local memory; host checks depth <= 62)
+#ifndef RT_OCTANT_SORT
+#define RT_OCTANT_SORT 1
+#endif
+#ifndef RT_SHADE_BLOCK_NOTE
+#endif
 #ifndef RT_EXTEND_MIN_BLOCKS
 #define RT_EXTEND_MIN_BLOCKS 8  // 64 registers per thread -> 32 resident warps per SM
 #endif
@@ -829,7 +834,11 @@ template <bool COUNT>
 __global__ void __launch_bounds__(RT_BLOCK) k_shade(rt_dev_scene sc, rt_frame fr, rt_ctrl* __restrict__ ctrl,
                                                     rt_paths cur, rt_paths nxt, rt_hits hits,
                                                     const uint32_t* __restrict__ queues, long long* __restrict__ accum) {
+#if RT_OCTANT_SORT
+  __shared__ uint32_t s_ocount[8][RT_WARPS];
+#else
   __shared__ uint32_t s_wcount[RT_WARPS];
+#endif
   __shared__ uint32_t s_base;
   // which class does this block serve?  class segments are padded to whole blocks
   uint32_t b = blockIdx.x;
@@ -966,7 +975,35 @@ __global__ void __launch_bounds__(RT_BLOCK) k_shade(rt_dev_scene sc, rt_frame fr
     alive = bounce < fr.path_depth && !(nT.x == 0.0f && nT.y == 0.0f && nT.z == 0.0f);
   }
 
-  // compact survivors into the next ray queue: ballot per warp, one atomic per block
+  // compact survivors into the next ray queue, one atomic per block.  Inside the block's output range the rays are
+  // grouped by the octant of their new direction (RT_OCTANT_SORT): rays that agree on the direction signs visit
+  // the children of a node in the same order, which keeps more lanes of a k_trace batch together.
+#if RT_OCTANT_SORT
+  const uint32_t oct = alive ? ((nd.x < 0.0f ? 1u : 0u) | (nd.y < 0.0f ? 2u : 0u) | (nd.z < 0.0f ? 4u : 0u)) : 8u;
+  uint32_t my_bal = 0;
+#pragma unroll
+  for (uint32_t k = 0; k < 8; ++k) {
+    uint32_t bk = __ballot_sync(0xFFFFFFFFu, oct == k);
+    if (lane == 0) s_ocount[k][warp] = __popc(bk);
+    if (oct == k) my_bal = bk;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    uint32_t total = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k)
+#pragma unroll
+      for (int w = 0; w < RT_WARPS; ++w) {
+        uint32_t c = s_ocount[k][w];
+        s_ocount[k][w] = total;
+        total += c;
+      }
+    s_base = total ? atomicAdd(&ctrl->n_next, total) : 0u;
+  }
+  __syncthreads();
+  if (alive) {
+    uint32_t pos = s_base + s_ocount[oct][warp] + __popc(my_bal & ((1u << lane) - 1u));
+#else
   uint32_t bal = __ballot_sync(0xFFFFFFFFu, alive);
   if (lane == 0) s_wcount[warp] = __popc(bal);
   __syncthreads();
@@ -983,6 +1020,7 @@ __global__ void __launch_bounds__(RT_BLOCK) k_shade(rt_dev_scene sc, rt_frame fr
   __syncthreads();
   if (alive) {
     uint32_t pos = s_base + s_wcount[warp] + __popc(bal & ((1u << lane) - 1u));
+#endif
     nxt.A[pos] = make_float4(no.x, no.y, no.z, nd.x);
     nxt.B[pos] = make_float4(nd.y, nd.z, nT.x, nT.y);
     nxt.C[pos] = make_float4(nT.z, __uint_as_float(pixel), __uint_as_float(sb), 0.0f);
