@@ -190,7 +190,9 @@ __device__ __forceinline__ bool slab(float4 lo, float4 hi, f3 inv, f3 oi, float 
 // d.x == 0 exactly, so this case is routine, not exotic.
 __device__ __forceinline__ float safe_rcp(float d) {
   float a = fabsf(d) < 1e-20f ? copysignf(1e-20f, d) : d;
-  return __fdividef(1.0f, a);
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(a));  // one MUFU.RCP; exactness is not needed here
+  return r;
 }
 __device__ __forceinline__ f3 approx_inv(f3 d) { return mk(safe_rcp(d.x), safe_rcp(d.y), safe_rcp(d.z)); }
 
@@ -227,6 +229,7 @@ struct Trav {
   int cur_obj;
   bool in_blas;
   uint32_t sbase;    // shared-space byte address of this thread's stack column ([depth][thread] layout)
+  uint32_t wbase;    // shared-space byte address of this thread's saved world-space (inv, oi), 6 words [k][thread]
   uint32_t* lstack;  // RT_LOCAL_STACK entries of local memory, declared by the kernel
   Best best;
   Cnt cnt;
@@ -254,15 +257,27 @@ struct Trav {
     inv = approx_inv(d);
     oi = mk(-o.x * inv.x, -o.y * inv.y, -o.z * inv.z);
   }
+  // the world-space reciprocal direction survives an instance visit in shared memory (cheaper than 3 reciprocals)
+  __device__ __forceinline__ void save_world_inv() const {
+    const float v[6] = {inv.x, inv.y, inv.z, oi.x, oi.y, oi.z};
+#pragma unroll
+    for (int k = 0; k < 6; ++k) asm volatile("st.shared.f32 [%0], %1;" ::"r"(wbase + k * (RT_BLOCK * 4u)), "f"(v[k]) : "memory");
+  }
+  __device__ __forceinline__ void load_world_inv() {
+    float v[6];
+#pragma unroll
+    for (int k = 0; k < 6; ++k) asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v[k]) : "r"(wbase + k * (RT_BLOCK * 4u)) : "memory");
+    inv = mk(v[0], v[1], v[2]);
+    oi = mk(v[3], v[4], v[5]);
+  }
   // pop the next entry; false when the stack is empty.  A RESTORE marker switches back to the
   // world-space ray and leaves entry = NONE (the caller pops again).
   __device__ __forceinline__ bool pop_next() {
     if (sp == 0) return false;
     entry = pop();
     if (entry == RT_ENTRY_RESTORE) {
-      f3 wo, wd;
-      world_ray(wo, wd);
-      set_space(wo, wd);
+      world_ray(o, d);
+      load_world_inv();
       in_blas = false;
       entry = RT_ENTRY_NONE;
     }
@@ -342,6 +357,7 @@ __device__ __forceinline__ void trav_leaf(const rt_dev_scene& sc, Trav& T) {
     uint32_t root = fbits(m7.x);
     if (root != RT_ENTRY_NONE) {
       T.push(RT_ENTRY_RESTORE);
+      T.save_world_inv();
       T.set_space(no, nd);
       T.in_blas = true;
       T.cur_obj = obj;
@@ -630,13 +646,14 @@ __global__ void __launch_bounds__(RT_BLOCK) k_raygen(rt_frame fr, rt_ctrl* __res
 template <bool COUNT>
 __global__ void __launch_bounds__(RT_BLOCK, RT_EXTEND_MIN_BLOCKS) k_trace(rt_dev_scene sc, rt_frame fr, rt_ctrl* __restrict__ ctrl,
                                                                         rt_paths cur, rt_hits hits) {
-  __shared__ uint32_t sstack[RT_SMEM_STACK * RT_BLOCK];
+  __shared__ uint32_t sstack[(RT_SMEM_STACK + 6) * RT_BLOCK];
   const uint32_t n_rays = ctrl->n_rays;
   const uint32_t lane = threadIdx.x & 31u;
   const uint32_t FULL = 0xFFFFFFFFu;
   uint32_t lstack[RT_LOCAL_STACK];
   Trav T;
   T.sbase = (uint32_t)__cvta_generic_to_shared(sstack) + threadIdx.x * 4u;
+  T.wbase = T.sbase + RT_SMEM_STACK * (RT_BLOCK * 4u);
   T.lstack = lstack;
   T.t_min = fr.t_min; T.t_max = fr.t_max;
   T.k0 = fr.k0; T.k1 = fr.k1;
