@@ -190,14 +190,12 @@ def run_reference(args):
 
 
 # ------------------------------------------------------------------------------------ GPU arm
-def extend_algorithmic_bytes(st) -> float:
-    """Algorithmic bytes of ALL k_extend launches of one frame (DESIGN.md "roofline accounting"):
-    32 B per BVH node fetched, 48 B per triangle record, 96 B of transforms per instance entered, 32 B per analytic
-    primitive record, 80 B per mesh shading record, 4 B per normal-map tap, plus the wavefront's own ray traffic:
-    48 B ray read (or written, for a new camera ray) + 20 B hit record + 4 B queue entry per ray."""
+def trace_algorithmic_bytes(st) -> float:
+    """Algorithmic bytes of ALL k_trace launches of one frame: 32 B per BVH node fetched,
+    48 B per triangle record, 96 B of transforms per instance entered, 32 B per analytic primitive record, plus the
+    wavefront's own traffic in this kernel: 48 B ray read + 20 B hit record written per ray."""
     return (32.0 * st["nodes_visited"] + 48.0 * st["tris_tested"] + 96.0 * st["instances_entered"]
-            + 32.0 * st["prims_tested"] + 80.0 * st["mesh_hits"] + 4.0 * st["extend_texel_taps"]
-            + 72.0 * st["rays"])
+            + 32.0 * st["prims_tested"] + 68.0 * st["rays"])
 
 
 def main():
@@ -329,10 +327,10 @@ def main():
             dist.destroy_process_group()
         return 0
 
-    # ---- roofline of the dominant kernel (k_extend), from CUDA events recorded around every launch in the timed region
+    # ---- roofline of the dominant kernel (k_trace), from CUDA events recorded around every launch in the timed region
     n_ext = max(stats_acc["extend_launches"], 1)
     ext_ms = stats_acc["ms_extend"] / n_ext
-    alg_bytes = extend_algorithmic_bytes(counted) / max(counted["extend_launches"], 1)
+    alg_bytes = trace_algorithmic_bytes(counted) / max(counted["extend_launches"], 1)
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -342,17 +340,17 @@ def main():
     achieved = alg_bytes / (ext_ms * 1e-3) / 1e9 if ext_ms > 0 else 0.0
     traffic = None
     try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "extend_dram_traffic.json"))).get(args.workload)
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "k_trace_dram_traffic.json"))).get(args.workload)
     except Exception:
         pass
     roofline = {
-        "kernel": "k_extend", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+        "kernel": "k_trace", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
         "frac": achieved / peak, "traffic": traffic,
         "peak_source": "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md)",
         "algorithmic_bytes_per_launch": alg_bytes, "ms_per_launch": ext_ms, "launches": int(n_ext),
         "share_of_step": stats_acc["ms_extend"] / max(stats_acc["ms_total"], 1e-9),
         "shade_share_of_step": stats_acc["ms_shade"] / max(stats_acc["ms_total"], 1e-9),
-        "bytes_per_ray": extend_algorithmic_bytes(counted) / max(counted["rays"], 1),
+        "bytes_per_ray": trace_algorithmic_bytes(counted) / max(counted["rays"], 1),
         "nodes_per_ray": counted["nodes_visited"] / max(counted["rays"], 1),
         "tris_per_ray": counted["tris_tested"] / max(counted["rays"], 1),
         "traversal_simt_efficiency": counted["nodes_visited"] / max(counted["warp_node_slots"], 1),

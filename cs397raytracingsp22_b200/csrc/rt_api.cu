@@ -285,12 +285,14 @@ int run_wavefront(rt_scene* s, const rt_frame& fr_in, unsigned long long total, 
       launches += 2;
       bool timed = use_events && timed_iters < kMaxTimedIters;
       cudaEvent_t e0 = nullptr, e1 = nullptr, e2 = nullptr;
+      rt::launch_raygen(fr, s->ctrl, s->paths[cur], st);
       if (timed) {
         if ((rc = next_event(e0)) != RT_OK || (rc = next_event(e1)) != RT_OK || (rc = next_event(e2)) != RT_OK) return rc;
         CUDA_TRY(cudaEventRecord(e0, st));
       }
-      rt::launch_extend(s->dev, fr, s->ctrl, s->paths[cur], s->hits, s->queues, count, true, s->persistent_blocks, st);
+      rt::launch_trace(s->dev, fr, s->ctrl, s->paths[cur], s->hits, count, s->persistent_blocks, st);  // dominant kernel
       if (timed) CUDA_TRY(cudaEventRecord(e1, st));
+      rt::launch_sort(s->dev, fr, s->ctrl, s->hits, s->queues, st);
       launches += 3; ++ext_launches;
       if (!single_iteration) {
         rt::launch_shade(s->dev, fr, s->ctrl, s->paths[cur], s->paths[nxt], s->hits, s->queues, d_accum, count, st);
@@ -679,7 +681,8 @@ static int trace_common(rt_scene* s, const rt_frame& fr, unsigned long long tota
   rt::launch_init(s->ctrl, ray_od ? 0ull : total, st);
   if (ray_od) CUDA_TRY(cudaMemcpyAsync(&s->ctrl->n_next, &n, 4, cudaMemcpyHostToDevice, st));
   rt::launch_advance(s->ctrl, f2.capacity, st);
-  rt::launch_extend(s->dev, f2, s->ctrl, s->paths[0], s->hits, s->queues, false, ray_od == nullptr, s->persistent_blocks, st);
+  if (!ray_od) rt::launch_raygen(f2, s->ctrl, s->paths[0], st);
+  rt::launch_trace(s->dev, f2, s->ctrl, s->paths[0], s->hits, false, s->persistent_blocks, st);
   rt::launch_surface(s->dev, f2, s->ctrl, s->paths[0], s->hits, dbg, st);
   CUDA_TRY(cudaGetLastError());
   std::vector<float> H0((size_t)n * 4), H1((size_t)n * 4), HH((size_t)n * 4);

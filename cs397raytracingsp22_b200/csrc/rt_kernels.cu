@@ -1115,15 +1115,18 @@ int trace_blocks_per_sm() {
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_trace<false>, RT_BLOCK, 0);
   return n > 0 ? n : 1;
 }
-// ray-gen for the new paths, closest hit for every ray, material-sorted queues
-void launch_extend(const rt_dev_scene& sc, const rt_frame& fr, rt_ctrl* ctrl, rt_paths cur, rt_hits hits,
-                   uint32_t* queues, bool count, bool have_new_rays, uint32_t persistent_blocks, cudaStream_t st) {
+void launch_raygen(const rt_frame& fr, rt_ctrl* ctrl, rt_paths cur, cudaStream_t st) {
+  k_raygen<<<(fr.capacity + RT_BLOCK - 1) / RT_BLOCK, RT_BLOCK, 0, st>>>(fr, ctrl, cur);
+}
+void launch_trace(const rt_dev_scene& sc, const rt_frame& fr, rt_ctrl* ctrl, rt_paths cur, rt_hits hits, bool count,
+                  uint32_t persistent_blocks, cudaStream_t st) {
   uint32_t full = (fr.capacity + RT_BLOCK - 1) / RT_BLOCK;
-  if (have_new_rays) k_raygen<<<full, RT_BLOCK, 0, st>>>(fr, ctrl, cur);
   uint32_t grid = full < persistent_blocks ? full : persistent_blocks;  // never more blocks than there could be rays
   if (count) k_trace<true><<<grid, RT_BLOCK, 0, st>>>(sc, fr, ctrl, cur, hits);
   else k_trace<false><<<grid, RT_BLOCK, 0, st>>>(sc, fr, ctrl, cur, hits);
-  k_sort<<<full, RT_BLOCK, 0, st>>>(sc, fr, ctrl, hits.obj, queues);
+}
+void launch_sort(const rt_dev_scene& sc, const rt_frame& fr, rt_ctrl* ctrl, rt_hits hits, uint32_t* queues, cudaStream_t st) {
+  k_sort<<<(fr.capacity + RT_BLOCK - 1) / RT_BLOCK, RT_BLOCK, 0, st>>>(sc, fr, ctrl, hits.obj, queues);
 }
 void launch_surface(const rt_dev_scene& sc, const rt_frame& fr, rt_ctrl* ctrl, rt_paths cur, rt_hits hits, rt_debug dbg,
                     cudaStream_t st) {

@@ -30,8 +30,10 @@ struct rt_debug {
 
 void launch_init(rt_ctrl* ctrl, unsigned long long total, cudaStream_t st);
 void launch_advance(rt_ctrl* ctrl, uint32_t capacity, cudaStream_t st);
-void launch_extend(const rt_dev_scene& sc, const rt_frame& fr, rt_ctrl* ctrl, rt_paths cur, rt_hits hits,
-                   uint32_t* queues, bool count, bool have_new_rays, uint32_t persistent_blocks, cudaStream_t st);
+void launch_raygen(const rt_frame& fr, rt_ctrl* ctrl, rt_paths cur, cudaStream_t st);
+void launch_trace(const rt_dev_scene& sc, const rt_frame& fr, rt_ctrl* ctrl, rt_paths cur, rt_hits hits, bool count,
+                  uint32_t persistent_blocks, cudaStream_t st);
+void launch_sort(const rt_dev_scene& sc, const rt_frame& fr, rt_ctrl* ctrl, rt_hits hits, uint32_t* queues, cudaStream_t st);
 void launch_surface(const rt_dev_scene& sc, const rt_frame& fr, rt_ctrl* ctrl, rt_paths cur, rt_hits hits, rt_debug dbg,
                     cudaStream_t st);
 int trace_blocks_per_sm();

@@ -111,8 +111,8 @@ typedef struct rt_stats {
   uint64_t rays;              /* closest-hit queries (= Scene::intersect_ray calls) */
   uint64_t iterations;        /* wavefront iterations                               */
   uint64_t kernel_launches;   /* kernels launched by this call                      */
-  uint64_t extend_launches;
-  uint64_t shade_launches;
+  uint64_t extend_launches;   /* k_trace launches that had rays                     */
+  uint64_t shade_launches;    /* k_shade launches that had rays                     */
   /* device counters, filled only with RT_OPT_COUNTERS */
   uint64_t nodes_visited;     /* 32-byte BVH nodes fetched                          */
   uint64_t tris_tested;       /* 48-byte triangle records fetched                   */
@@ -126,8 +126,8 @@ typedef struct rt_stats {
                                  nodes_visited / warp_node_slots = SIMT efficiency of traversal */
   /* CUDA-event times on the render stream, milliseconds */
   double ms_total;
-  double ms_extend;
-  double ms_shade;
+  double ms_extend;           /* k_trace only (the dominant kernel)                 */
+  double ms_shade;            /* k_sort + k_shade                                   */
   double ms_resolve;
   uint64_t h2d_bytes;         /* bytes copied host->device by this call             */
   uint64_t d2h_bytes;         /* bytes copied device->host by this call             */
