@@ -56,6 +56,5 @@ def test_cpp_run_renders_the_reference_scene(tmp_path, gpu):
     assert img.mean() > 2 and (img.max(axis=2) > 0).mean() > 0.2      # something was rendered
     # deterministic: same seed, same image
     out2 = tmp_path / "render2.tga"
-    subprocess.run([exe, _unpack_objs(tmp_path / ".." / (tmp_path.name + "b")) if False else str(tmp_path / "obj"), str(out2), "96", "96", "16"], check=True,
-                   capture_output=True)
+    subprocess.run([exe, str(tmp_path / "obj"), str(out2), "96", "96", "16"], check=True, capture_output=True)
     assert np.array_equal(_ffi.tga_decode(out2.read_bytes()), img)
