@@ -265,3 +265,50 @@ def test_counters_and_timers(gpu, small_scenes):
     assert st.ms_total > 0 and st.ms_extend > 0 and st.ms_shade > 0 and st.ms_extend + st.ms_shade <= st.ms_total * 1.05
     assert st.kernel_launches >= 4 * st.iterations
     assert g.device_bytes() > 100_000
+
+
+def _rank_worker(rank, world, port, q):
+    """One rank of the N>1 path with REAL rendering: both ranks share cuda:0 here (the test box has one GPU), so the
+    accumulators travel through gloo on the CPU; on a multi-GPU box bench.py does the same over NCCL."""
+    import os
+    import torch
+    import torch.distributed as dist
+    from cs397raytracingsp22_b200 import scenes
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        sc = scenes.make_scene("c4", width=96, height=54, spp=16, map_size=128)
+        g = sc.commit(0)
+        cam = sc.camera.to_c()
+        dev = torch.device("cuda", 0)
+        acc = D.new_accum(cam.screen_width, cam.screen_height, dev)
+        D.render_shard(g, cam, D.shard_opts(rank, world, SEED, "samples"), acc)
+        torch.cuda.synchronize()
+        host = acc.cpu()
+        D.reduce_accum(host, dst=0)
+        if rank == 0:
+            full = D.new_accum(cam.screen_width, cam.screen_height, dev)
+            D.render_shard(g, cam, D.shard_opts(0, 1, SEED, "all"), full)
+            torch.cuda.synchronize()
+            q.put(bool(torch.equal(full.cpu(), host)) and int(host.abs().sum()) > 0)
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(300)
+def test_two_ranks_render_and_reduce_to_the_single_gpu_frame(gpu):
+    import socket
+    import torch.multiprocessing as mp
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_rank_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    ok = q.get(timeout=240)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert ok, "sum of the two ranks' accumulators differs from the single-GPU accumulator"
