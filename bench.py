@@ -352,6 +352,7 @@ def main():
         "shade_share_of_step": stats_acc["ms_shade"] / max(stats_acc["ms_total"], 1e-9),
         "bytes_per_ray": trace_algorithmic_bytes(counted) / max(counted["rays"], 1),
         "nodes_per_ray": counted["nodes_visited"] / max(counted["rays"], 1),
+        "tlas_nodes_per_ray": counted["tlas_nodes_visited"] / max(counted["rays"], 1),
         "tris_per_ray": counted["tris_tested"] / max(counted["rays"], 1),
         "traversal_simt_efficiency": counted["nodes_visited"] / max(counted["warp_node_slots"], 1),
         "note": "the lowered scene fits in L2, so DRAM traffic is far below algorithmic bytes; the kernel is "

@@ -52,6 +52,7 @@ class rt_render_opts(C.Structure):
 class rt_stats(C.Structure):
     _fields_ = [(n, C.c_uint64) for n in (
         "samples", "rays", "iterations", "kernel_launches", "extend_launches", "shade_launches", "nodes_visited",
+        "tlas_nodes_visited",
         "tris_tested", "instances_entered", "prims_tested", "mesh_hits", "texel_taps", "extend_texel_taps",
         "material_fetches", "warp_node_slots")] + [
         (n, C.c_double) for n in ("ms_total", "ms_extend", "ms_shade", "ms_resolve")] + [
@@ -59,6 +60,11 @@ class rt_stats(C.Structure):
 
     def as_dict(self) -> dict:
         return {n: getattr(self, n) for n, _ in self._fields_}
+
+
+class rt_lower_info(C.Structure):
+    _fields_ = [("bytes", C.c_uint64), ("nodes", C.c_uint32), ("tris", C.c_uint32), ("objects", C.c_uint32),
+                ("unbounded", C.c_uint32), ("tlas_depth", C.c_uint32), ("max_blas_depth", C.c_uint32)]
 
 
 class rt_obj_mesh(C.Structure):
@@ -87,6 +93,7 @@ SIGNATURES = {
     "rt_add_triangle": (C.c_int, [_P, _F, _F, _F, C.c_int]),
     "rt_add_plane": (C.c_int, [_P, _F, _F, C.c_int]),
     "rt_add_volume_sphere": (C.c_int, [_P, _F, C.c_float, C.c_float, C.c_int]),
+    "rt_scene_lower": (C.c_int, [_P, C.POINTER(rt_lower_info)]),
     "rt_commit": (C.c_int, [_P, C.c_int]),
     "rt_scene_device_bytes": (C.c_uint64, [_P]),
     "rt_scene_upload": (C.c_int, [_P]),
@@ -263,6 +270,12 @@ class GpuBackend:
     def add_volume_sphere(self, center, radius, density, material) -> int:
         return check(self.lib.rt_add_volume_sphere(self.handle, fptr(f3(center)), float(radius), float(density),
                                                    material))
+
+    def lower_info(self) -> dict:
+        """Host-only lowering (no GPU needed): sizes and depths of what rt_commit would upload."""
+        info = rt_lower_info()
+        check(self.lib.rt_scene_lower(self.handle, C.byref(info)))
+        return {n: getattr(info, n) for n, _ in info._fields_}
 
     # -- device
     def commit(self, device: int = 0):

@@ -34,6 +34,11 @@ struct DevBuf {
 };
 }  // namespace
 
+#define RT_MAX_LANES 4
+#ifndef RT_DEFAULT_LANES
+#define RT_DEFAULT_LANES 1
+#endif
+
 struct rt_scene {
   std::vector<rt::HostTexture> textures;
   std::vector<rt_material_desc> materials;
@@ -49,18 +54,25 @@ struct rt_scene {
   DevBuf d_nodes, d_tris, d_shade, d_objects, d_mats, d_textures, d_texels, d_planes;
   rt_dev_scene dev{};
 
-  // wavefront state
-  uint32_t capacity = 0;
-  rt::rt_paths paths[2] = {};
-  rt::rt_hits hits = {};
-  uint32_t* queues = nullptr;
-  rt_ctrl* ctrl = nullptr;
-  rt_ctrl* h_ctrl = nullptr;     // pinned
-  uint32_t* h_done = nullptr;    // pinned poll slots
-  cudaEvent_t poll_ev[2] = {nullptr, nullptr};
-  std::vector<cudaEvent_t> events;
+  // wavefront state: one or more independent "lanes" (ray queues + control block + stream).  Several lanes let
+  // the tail of one lane's k_trace and its bandwidth-bound k_shade overlap the other lane's traversal.
+  struct Lane {
+    uint32_t capacity = 0;
+    rt::rt_paths paths[2] = {};
+    rt::rt_hits hits = {};
+    uint32_t* queues = nullptr;
+    rt_ctrl* ctrl = nullptr;
+    rt_ctrl* h_ctrl = nullptr;   // pinned
+    uint32_t* h_done = nullptr;  // pinned poll slots
+    cudaEvent_t poll_ev[2] = {nullptr, nullptr};
+    cudaEvent_t end_ev = nullptr;
+    std::vector<cudaEvent_t> events;
+    cudaStream_t stream = nullptr;
+  };
+  Lane lanes[RT_MAX_LANES];
   cudaStream_t own_stream = nullptr;
-  uint32_t persistent_blocks = 148 * 8;  // k_extend grid: SM count x resident blocks per SM
+  cudaEvent_t begin_ev = nullptr;
+  uint32_t persistent_blocks = 148 * 8;  // k_trace grid: SM count x resident blocks per SM
   // scratch for host-buffer entry points
   DevBuf d_accum, d_linear, d_rgb8, d_dbg;
 };
@@ -86,47 +98,65 @@ int upload(DevBuf& b, const void* src, size_t bytes, cudaStream_t st) {
   return RT_OK;
 }
 
-void free_wavefront(rt_scene* s) {
+void free_lane(rt_scene::Lane& L) {
   for (int k = 0; k < 2; ++k) {
-    if (s->paths[k].A) cudaFree(s->paths[k].A);
-    if (s->paths[k].B) cudaFree(s->paths[k].B);
-    if (s->paths[k].C) cudaFree(s->paths[k].C);
-    s->paths[k] = rt::rt_paths{};
+    if (L.paths[k].A) cudaFree(L.paths[k].A);
+    if (L.paths[k].B) cudaFree(L.paths[k].B);
+    if (L.paths[k].C) cudaFree(L.paths[k].C);
+    L.paths[k] = rt::rt_paths{};
   }
-  if (s->hits.H) cudaFree(s->hits.H);
-  if (s->hits.obj) cudaFree(s->hits.obj);
-  s->hits = rt::rt_hits{};
-  if (s->queues) cudaFree(s->queues);
-  s->queues = nullptr;
-  s->capacity = 0;
+  if (L.hits.H) cudaFree(L.hits.H);
+  if (L.hits.obj) cudaFree(L.hits.obj);
+  L.hits = rt::rt_hits{};
+  if (L.queues) cudaFree(L.queues);
+  L.queues = nullptr;
+  L.capacity = 0;
+}
+void free_wavefront(rt_scene* s) {
+  for (auto& L : s->lanes) free_lane(L);
 }
 
-int ensure_wavefront(rt_scene* s, uint32_t capacity) {
-  if (!s->ctrl) {
-    CUDA_TRY(cudaMalloc((void**)&s->ctrl, sizeof(rt_ctrl)));
-    CUDA_TRY(cudaMallocHost((void**)&s->h_ctrl, sizeof(rt_ctrl)));
-    CUDA_TRY(cudaMallocHost((void**)&s->h_done, 2 * sizeof(uint32_t)));
-    CUDA_TRY(cudaEventCreateWithFlags(&s->poll_ev[0], cudaEventDisableTiming));
-    CUDA_TRY(cudaEventCreateWithFlags(&s->poll_ev[1], cudaEventDisableTiming));
-    CUDA_TRY(cudaStreamCreateWithFlags(&s->own_stream, cudaStreamNonBlocking));
-    int sms = 0;
-    CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, s->device));
-    s->persistent_blocks = (uint32_t)(sms * rt::trace_blocks_per_sm());
-  }
-  if (s->capacity >= capacity && s->queues) return RT_OK;
-  free_wavefront(s);
-  size_t n = capacity;
-  for (int k = 0; k < 2; ++k) {
-    CUDA_TRY(cudaMalloc((void**)&s->paths[k].A, n * 16));
-    CUDA_TRY(cudaMalloc((void**)&s->paths[k].B, n * 16));
-    CUDA_TRY(cudaMalloc((void**)&s->paths[k].C, n * 16));
-  }
-  CUDA_TRY(cudaMalloc((void**)&s->hits.H, n * 16));
-  CUDA_TRY(cudaMalloc((void**)&s->hits.obj, n * 4));
-  CUDA_TRY(cudaMalloc((void**)&s->queues, n * 4 * RT_NUM_CLASSES));
-  s->capacity = capacity;
+int ensure_runtime(rt_scene* s) {
+  if (s->own_stream) return RT_OK;
+  CUDA_TRY(cudaStreamCreateWithFlags(&s->own_stream, cudaStreamNonBlocking));
+  CUDA_TRY(cudaEventCreateWithFlags(&s->begin_ev, cudaEventDisableTiming));
+  int sms = 0;
+  CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, s->device));
+  int per_sm = rt::trace_blocks_per_sm();
+  if (const char* e = std::getenv("RT_TRACE_BLOCKS")) per_sm = std::max(1, std::min(per_sm, std::atoi(e)));
+  s->persistent_blocks = (uint32_t)(sms * per_sm);
   return RT_OK;
 }
+
+int ensure_lane(rt_scene* s, int li, uint32_t capacity) {
+  int rc = ensure_runtime(s);
+  if (rc != RT_OK) return rc;
+  rt_scene::Lane& L = s->lanes[li];
+  if (!L.ctrl) {
+    CUDA_TRY(cudaMalloc((void**)&L.ctrl, sizeof(rt_ctrl)));
+    CUDA_TRY(cudaMallocHost((void**)&L.h_ctrl, sizeof(rt_ctrl)));
+    CUDA_TRY(cudaMallocHost((void**)&L.h_done, 2 * sizeof(uint32_t)));
+    CUDA_TRY(cudaEventCreateWithFlags(&L.poll_ev[0], cudaEventDisableTiming));
+    CUDA_TRY(cudaEventCreateWithFlags(&L.poll_ev[1], cudaEventDisableTiming));
+    CUDA_TRY(cudaEventCreateWithFlags(&L.end_ev, cudaEventDisableTiming));
+    CUDA_TRY(cudaStreamCreateWithFlags(&L.stream, cudaStreamNonBlocking));
+  }
+  if (L.capacity >= capacity && L.queues) return RT_OK;
+  free_lane(L);
+  size_t n = capacity;
+  for (int k = 0; k < 2; ++k) {
+    CUDA_TRY(cudaMalloc((void**)&L.paths[k].A, n * 16));
+    CUDA_TRY(cudaMalloc((void**)&L.paths[k].B, n * 16));
+    CUDA_TRY(cudaMalloc((void**)&L.paths[k].C, n * 16));
+  }
+  CUDA_TRY(cudaMalloc((void**)&L.hits.H, n * 16));
+  CUDA_TRY(cudaMalloc((void**)&L.hits.obj, n * 4));
+  CUDA_TRY(cudaMalloc((void**)&L.queues, n * 4 * RT_NUM_CLASSES));
+  L.capacity = capacity;
+  return RT_OK;
+}
+// kept for the entry points that only need the runtime objects / lane 0
+int ensure_wavefront(rt_scene* s, uint32_t capacity) { return ensure_lane(s, 0, capacity); }
 
 int check_camera(const rt_camera* cam) {
   if (!cam) return fail(RT_ERR_INVALID, "camera is NULL");
@@ -243,125 +273,167 @@ int set_device(rt_scene* s) {
   return RT_OK;
 }
 
-// The wavefront loop.  Launches are asynchronous; the device decides how many rays each
-// iteration has.  The host only peeks at a `done` flag every few iterations, two polls deep, so
-// the stream never drains.
+// The wavefront loop.  Launches are asynchronous; the device decides how many rays each iteration has.  The host
+// only peeks at a `done` flag every few iterations, two polls deep, so the streams never drain.  With several lanes
+// the frame's work indices are cut into contiguous ranges, one per lane, and the lanes' iterations are enqueued
+// round-robin on their own streams.
 int run_wavefront(rt_scene* s, const rt_frame& fr_in, unsigned long long total, long long* d_accum, bool count,
-                  bool use_events, cudaStream_t st, rt_stats* stats) {
-  const bool single_iteration = false;
+                  bool use_events, cudaStream_t user_st, int nlanes, rt_stats* stats) {
+  int rc;
+  nlanes = std::max(1, std::min(nlanes, RT_MAX_LANES));
+  if (total < (unsigned long long)nlanes * 65536ull) nlanes = 1;  // tiny jobs: one lane
   rt_frame fr = fr_in;
-  int rc = ensure_wavefront(s, fr.capacity);
-  if (rc != RT_OK) return rc;
-  fr.capacity = s->capacity >= fr.capacity ? fr.capacity : s->capacity;
+  fr.capacity = std::max<uint32_t>(128u, (fr.capacity / (uint32_t)nlanes + 127u) / 128u * 128u);
+  for (int li = 0; li < nlanes; ++li)
+    if ((rc = ensure_lane(s, li, fr.capacity)) != RT_OK) return rc;
   const int kChunk = 8;
-  size_t ev_used = 0;
-  auto next_event = [&](cudaEvent_t& ev) -> int {
-    if (ev_used == s->events.size()) {
+  const size_t kMaxTimedIters = 1u << 14;
+  struct LaneRun {
+    size_t ev_used = 0, ev_iter_base = 0, timed_iters = 0;
+    uint64_t launches = 0, ext = 0, shd = 0;
+    unsigned long long it = 0;
+    int chunk = 0;
+    bool done = false;
+    cudaStream_t st = nullptr;
+  } run[RT_MAX_LANES];
+  auto next_event = [&](int li, cudaEvent_t& ev) -> int {
+    rt_scene::Lane& L = s->lanes[li];
+    if (run[li].ev_used == L.events.size()) {
       cudaEvent_t e;
       CUDA_TRY(cudaEventCreate(&e));
-      s->events.push_back(e);
+      L.events.push_back(e);
     }
-    ev = s->events[ev_used++];
+    ev = L.events[run[li].ev_used++];
     return RT_OK;
   };
-  const size_t kMaxTimedIters = 1u << 15;
+  // frame begin / end are timed on the caller's stream; lane streams fork from it and join it again
   cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
-  if ((rc = next_event(ev_begin)) != RT_OK) return rc;
-  if ((rc = next_event(ev_end)) != RT_OK) return rc;
-  CUDA_TRY(cudaEventRecord(ev_begin, st));
-  rt::launch_init(s->ctrl, total, st);
-  uint64_t launches = 1, ext_launches = 0, shd_launches = 0;
-  s->h_done[0] = s->h_done[1] = 0;
-  int chunk = 0;
-  bool done = false;
-  size_t timed_iters = 0;
-  size_t ev_iter_base = ev_used;
-  unsigned long long max_iters = single_iteration ? 1 : ~0ull;
-  unsigned long long it = 0;
-  while (!done && it < max_iters) {
-    for (int k = 0; k < kChunk && it < max_iters; ++k, ++it) {
-      int cur = (int)(it & 1), nxt = cur ^ 1;
-      rt::launch_advance(s->ctrl, fr.capacity, st);
-      launches += 2;
-      bool timed = use_events && timed_iters < kMaxTimedIters;
-      cudaEvent_t e0 = nullptr, e1 = nullptr, e2 = nullptr;
-      rt::launch_raygen(fr, s->ctrl, s->paths[cur], st);
-      if (timed) {
-        if ((rc = next_event(e0)) != RT_OK || (rc = next_event(e1)) != RT_OK || (rc = next_event(e2)) != RT_OK) return rc;
-        CUDA_TRY(cudaEventRecord(e0, st));
-      }
-      rt::launch_trace(s->dev, fr, s->ctrl, s->paths[cur], s->hits, count, s->persistent_blocks, st);  // dominant kernel
-      if (timed) CUDA_TRY(cudaEventRecord(e1, st));
-      rt::launch_sort(s->dev, fr, s->ctrl, s->hits, s->queues, st);
-      launches += 3; ++ext_launches;
-      if (!single_iteration) {
-        rt::launch_shade(s->dev, fr, s->ctrl, s->paths[cur], s->paths[nxt], s->hits, s->queues, d_accum, count, st);
-        ++launches; ++shd_launches;
-      }
-      if (timed) {
-        CUDA_TRY(cudaEventRecord(e2, st));
-        ++timed_iters;
-      }
-    }
-    if (single_iteration) break;
-    // poll: copy the done flag written by k_advance, two chunks deep
-    int slot = chunk & 1;
-    if (chunk >= 2) {
-      CUDA_TRY(cudaEventSynchronize(s->poll_ev[slot]));
-      if (s->h_done[slot]) done = true;
-    }
-    if (!done) {
-      CUDA_TRY(cudaMemcpyAsync(&s->h_done[slot], &s->ctrl->done, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
-      CUDA_TRY(cudaEventRecord(s->poll_ev[slot], st));
-    }
-    ++chunk;
+  if ((rc = next_event(0, ev_begin)) != RT_OK || (rc = next_event(0, ev_end)) != RT_OK) return rc;
+  CUDA_TRY(cudaEventRecord(ev_begin, user_st));
+  if (nlanes > 1) CUDA_TRY(cudaEventRecord(s->begin_ev, user_st));
+  for (int li = 0; li < nlanes; ++li) {
+    rt_scene::Lane& L = s->lanes[li];
+    run[li].st = nlanes == 1 ? user_st : L.stream;
+    if (nlanes > 1) CUDA_TRY(cudaStreamWaitEvent(run[li].st, s->begin_ev, 0));
+    unsigned long long b = total * (unsigned long long)li / (unsigned long long)nlanes;
+    unsigned long long e = total * (unsigned long long)(li + 1) / (unsigned long long)nlanes;
+    rt::launch_init(L.ctrl, b, e, run[li].st);
+    run[li].launches = 1;
+    run[li].ev_iter_base = run[li].ev_used;
+    L.h_done[0] = L.h_done[1] = 0;
   }
-  CUDA_TRY(cudaEventRecord(ev_end, st));
-  CUDA_TRY(cudaMemcpyAsync(s->h_ctrl, s->ctrl, sizeof(rt_ctrl), cudaMemcpyDeviceToHost, st));
-  CUDA_TRY(cudaStreamSynchronize(st));
+  int live = nlanes;
+  while (live > 0) {
+    for (int k = 0; k < kChunk; ++k)
+      for (int li = 0; li < nlanes; ++li) {
+        LaneRun& R = run[li];
+        if (R.done) continue;
+        rt_scene::Lane& L = s->lanes[li];
+        cudaStream_t st = R.st;
+        int cur = (int)(R.it & 1), nxt = cur ^ 1;
+        rt::launch_advance(L.ctrl, fr.capacity, st);
+        bool timed = use_events && R.timed_iters < kMaxTimedIters;
+        cudaEvent_t e0 = nullptr, e1 = nullptr, e2 = nullptr;
+        rt::launch_raygen(fr, L.ctrl, L.paths[cur], st);
+        if (timed) {
+          if ((rc = next_event(li, e0)) != RT_OK || (rc = next_event(li, e1)) != RT_OK || (rc = next_event(li, e2)) != RT_OK) return rc;
+          CUDA_TRY(cudaEventRecord(e0, st));
+        }
+        rt::launch_trace(s->dev, fr, L.ctrl, L.paths[cur], L.hits, count, s->persistent_blocks, st);  // dominant kernel
+        if (timed) CUDA_TRY(cudaEventRecord(e1, st));
+        rt::launch_sort(s->dev, fr, L.ctrl, L.hits, L.queues, st);
+        rt::launch_shade(s->dev, fr, L.ctrl, L.paths[cur], L.paths[nxt], L.hits, L.queues, d_accum, count, st);
+        if (timed) {
+          CUDA_TRY(cudaEventRecord(e2, st));
+          ++R.timed_iters;
+        }
+        R.launches += 6; ++R.ext; ++R.shd; ++R.it;
+      }
+    // poll each lane: copy the done flag written by k_advance, two chunks deep
+    for (int li = 0; li < nlanes; ++li) {
+      LaneRun& R = run[li];
+      if (R.done) continue;
+      rt_scene::Lane& L = s->lanes[li];
+      int slot = R.chunk & 1;
+      if (R.chunk >= 2) {
+        CUDA_TRY(cudaEventSynchronize(L.poll_ev[slot]));
+        if (L.h_done[slot]) {
+          R.done = true;
+          --live;
+        }
+      }
+      if (!R.done) {
+        CUDA_TRY(cudaMemcpyAsync(&L.h_done[slot], &L.ctrl->done, sizeof(uint32_t), cudaMemcpyDeviceToHost, R.st));
+        CUDA_TRY(cudaEventRecord(L.poll_ev[slot], R.st));
+      }
+      ++R.chunk;
+    }
+  }
+  for (int li = 0; li < nlanes; ++li) {
+    rt_scene::Lane& L = s->lanes[li];
+    CUDA_TRY(cudaMemcpyAsync(L.h_ctrl, L.ctrl, sizeof(rt_ctrl), cudaMemcpyDeviceToHost, run[li].st));
+    if (nlanes > 1) {
+      CUDA_TRY(cudaEventRecord(L.end_ev, run[li].st));
+      CUDA_TRY(cudaStreamWaitEvent(user_st, L.end_ev, 0));
+    }
+  }
+  CUDA_TRY(cudaEventRecord(ev_end, user_st));
+  CUDA_TRY(cudaStreamSynchronize(user_st));
   CUDA_TRY(cudaGetLastError());
-  if (!single_iteration && !s->h_ctrl->done && s->h_ctrl->cursor != s->h_ctrl->total)
-    return fail(RT_ERR_CUDA, "wavefront loop ended before all work was issued");
+  for (int li = 0; li < nlanes; ++li) {
+    const rt_ctrl& c = *s->lanes[li].h_ctrl;
+    if (!c.done && c.cursor != c.total) return fail(RT_ERR_CUDA, "wavefront loop ended before all work was issued");
+  }
   if (stats) {
-    const rt_ctrl& c = *s->h_ctrl;
-    stats->samples += c.n_samples - c.counters[7];
-    stats->rays += c.n_rays_total - c.counters[7];
-    stats->iterations += c.iterations;
-    stats->kernel_launches += launches;
-    // report the launches that did work, not the no-op tail queued behind the `done` poll
-    stats->extend_launches += std::min<uint64_t>(ext_launches, c.iterations);
-    stats->shade_launches += std::min<uint64_t>(shd_launches, c.iterations);
-    stats->nodes_visited += c.counters[0];
-    stats->tris_tested += c.counters[1];
-    stats->instances_entered += c.counters[2];
-    stats->prims_tested += c.counters[3];
-    stats->mesh_hits += c.counters[4];
-    stats->texel_taps += c.counters[5] + c.counters[8];
-    stats->extend_texel_taps += c.counters[8];
-    stats->material_fetches += c.counters[6];
-    stats->warp_node_slots += c.counters[9];
     float ms = 0.0f;
     cudaEventElapsedTime(&ms, ev_begin, ev_end);
     stats->ms_total += ms;
-    // only iterations that actually had rays count as launches of the dominant kernel
-    double me = 0.0, msd = 0.0;
-    size_t live = std::min<size_t>(timed_iters, c.iterations);
-    for (size_t i = 0; i < live; ++i) {
-      float a = 0.0f, b = 0.0f;
-      cudaEventElapsedTime(&a, s->events[ev_iter_base + 3 * i], s->events[ev_iter_base + 3 * i + 1]);
-      cudaEventElapsedTime(&b, s->events[ev_iter_base + 3 * i + 1], s->events[ev_iter_base + 3 * i + 2]);
-      me += a;
-      msd += b;
+    for (int li = 0; li < nlanes; ++li) {
+      const rt_scene::Lane& L = s->lanes[li];
+      const LaneRun& R = run[li];
+      const rt_ctrl& c = *L.h_ctrl;
+      stats->samples += c.n_samples - c.counters[7];
+      stats->rays += c.n_rays_total - c.counters[7];
+      stats->iterations += c.iterations;
+      stats->kernel_launches += R.launches;
+      // report the launches that did work, not the no-op tail queued behind the `done` poll
+      stats->extend_launches += std::min<uint64_t>(R.ext, c.iterations);
+      stats->shade_launches += std::min<uint64_t>(R.shd, c.iterations);
+      stats->nodes_visited += c.counters[0];
+      stats->tris_tested += c.counters[1];
+      stats->instances_entered += c.counters[2];
+      stats->prims_tested += c.counters[3];
+      stats->mesh_hits += c.counters[4];
+      stats->texel_taps += c.counters[5] + c.counters[8];
+      stats->extend_texel_taps += c.counters[8];
+      stats->material_fetches += c.counters[6];
+      stats->warp_node_slots += c.counters[9];
+      stats->tlas_nodes_visited += c.counters[10];
+      // only iterations that actually had rays count as launches of the dominant kernel
+      double me = 0.0, msd = 0.0;
+      size_t live_it = std::min<size_t>(R.timed_iters, c.iterations);
+      for (size_t i = 0; i < live_it; ++i) {
+        float a = 0.0f, b = 0.0f;
+        cudaEventElapsedTime(&a, L.events[R.ev_iter_base + 3 * i], L.events[R.ev_iter_base + 3 * i + 1]);
+        cudaEventElapsedTime(&b, L.events[R.ev_iter_base + 3 * i + 1], L.events[R.ev_iter_base + 3 * i + 2]);
+        me += a;
+        msd += b;
+      }
+      if (live_it && live_it < c.iterations) {  // more iterations than event slots: scale up
+        double f = (double)c.iterations / (double)live_it;
+        me *= f;
+        msd *= f;
+      }
+      stats->ms_extend += me;
+      stats->ms_shade += msd;
     }
-    if (live && live < c.iterations) {  // more iterations than event slots: scale up
-      double f = (double)c.iterations / (double)live;
-      me *= f;
-      msd *= f;
-    }
-    stats->ms_extend += me;
-    stats->ms_shade += msd;
   }
   return RT_OK;
+}
+
+int default_lanes() {
+  if (const char* e = std::getenv("RT_LANES")) return std::max(1, std::min(RT_MAX_LANES, std::atoi(e)));
+  return RT_DEFAULT_LANES;
 }
 
 }  // namespace
@@ -391,11 +463,16 @@ void rt_scene_destroy(rt_scene* s) {
     free_buf(s->d_nodes); free_buf(s->d_tris); free_buf(s->d_shade); free_buf(s->d_objects);
     free_buf(s->d_mats); free_buf(s->d_textures); free_buf(s->d_texels); free_buf(s->d_planes);
     free_buf(s->d_accum); free_buf(s->d_linear); free_buf(s->d_rgb8); free_buf(s->d_dbg);
-    if (s->ctrl) cudaFree(s->ctrl);
-    if (s->h_ctrl) cudaFreeHost(s->h_ctrl);
-    if (s->h_done) cudaFreeHost(s->h_done);
-    for (auto e : s->events) cudaEventDestroy(e);
-    for (auto e : s->poll_ev) if (e) cudaEventDestroy(e);
+    for (auto& L : s->lanes) {
+      if (L.ctrl) cudaFree(L.ctrl);
+      if (L.h_ctrl) cudaFreeHost(L.h_ctrl);
+      if (L.h_done) cudaFreeHost(L.h_done);
+      for (auto e : L.events) cudaEventDestroy(e);
+      for (auto e : L.poll_ev) if (e) cudaEventDestroy(e);
+      if (L.end_ev) cudaEventDestroy(L.end_ev);
+      if (L.stream) cudaStreamDestroy(L.stream);
+    }
+    if (s->begin_ev) cudaEventDestroy(s->begin_ev);
     if (s->own_stream) cudaStreamDestroy(s->own_stream);
   }
   delete s;
@@ -537,6 +614,29 @@ int rt_scene_upload(rt_scene* s) {
   return RT_OK;
 }
 
+int rt_scene_lower(rt_scene* s, rt_lower_info* info) {
+  if (!s) return fail(RT_ERR_INVALID, "scene is NULL");
+  std::string err;
+  int rc = rt::lower_scene(s->textures, s->materials, s->meshes, s->objects, s->low, err);
+  if (rc != RT_OK) return fail(rc, err);
+  s->lowered = true;
+  if (info) {
+    const rt::Lowered& L = s->low;
+    info->bytes = L.bytes();
+    info->nodes = (uint32_t)(L.nodes.size() / RT_NODE_QUADS);
+    info->tris = 0;
+    info->max_blas_depth = 0;
+    for (const auto& m : s->meshes) {
+      info->tris += m.n_reachable;
+      info->max_blas_depth = std::max(info->max_blas_depth, m.depth);
+    }
+    info->objects = (uint32_t)s->objects.size();
+    info->unbounded = (L.planes.size() == 1 && L.planes[0] < 0) ? 0u : (uint32_t)L.planes.size();
+    info->tlas_depth = L.tlas_depth;
+  }
+  return RT_OK;
+}
+
 int rt_commit(rt_scene* s, int device) {
   if (!s) return fail(RT_ERR_INVALID, "scene is NULL");
   int n = 0;
@@ -546,10 +646,8 @@ int rt_commit(rt_scene* s, int device) {
                                  (e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0"));
   if (device < 0 || device >= n) return fail(RT_ERR_INVALID, "rt_commit: bad device index");
   if (s->device >= 0 && s->device != device) return fail(RT_ERR_INVALID, "rt_commit: scene is already bound to another device");
-  std::string err;
-  int rc = rt::lower_scene(s->textures, s->materials, s->meshes, s->objects, s->low, err);
-  if (rc != RT_OK) return fail(rc, err);
-  s->lowered = true;
+  int rc = rt_scene_lower(s, nullptr);
+  if (rc != RT_OK) return rc;
   s->device = device;
   return rt_scene_upload(s);
 }
@@ -573,14 +671,10 @@ int rt_render_accum(rt_scene* s, const rt_camera* cam, const rt_render_opts* opt
   fr.capacity = pick_capacity(total, o.wavefront);
   if (stats) std::memset(stats, 0, sizeof *stats);
   if (total == 0) return RT_OK;
+  if ((rc = ensure_runtime(s)) != RT_OK) return rc;
   cudaStream_t st = stream ? (cudaStream_t)stream : s->own_stream;
-  if (!stream) {
-    // first use: own_stream is created by ensure_wavefront
-    if ((rc = ensure_wavefront(s, fr.capacity)) != RT_OK) return rc;
-    st = s->own_stream;
-  }
   return run_wavefront(s, fr, total, (long long*)d_accum, (o.flags & RT_OPT_COUNTERS) != 0,
-                       (o.flags & RT_OPT_NO_EVENTS) == 0, st, stats);
+                       (o.flags & RT_OPT_NO_EVENTS) == 0, st, default_lanes(), stats);
 }
 
 int rt_resolve(rt_scene* s, const rt_camera* cam, const void* d_accum, uint32_t total_spp, float* d_out_linear,
@@ -602,7 +696,7 @@ int rt_render(rt_scene* s, const rt_camera* cam, const rt_render_opts* opts, flo
   if ((rc = check_camera(cam)) != RT_OK) return rc;
   size_t npix = (size_t)cam->screen_width * cam->screen_height;
   if ((rc = ensure_buf(s->d_accum, rt_accum_bytes(cam->screen_width, cam->screen_height))) != RT_OK) return rc;
-  if ((rc = ensure_wavefront(s, 128)) != RT_OK) return rc;
+  if ((rc = ensure_runtime(s)) != RT_OK) return rc;
   cudaStream_t st = s->own_stream;
   CUDA_TRY(cudaMemsetAsync(s->d_accum.p, 0, rt_accum_bytes(cam->screen_width, cam->screen_height), st));
   rt_stats local{};
@@ -651,6 +745,7 @@ static int trace_common(rt_scene* s, const rt_frame& fr, unsigned long long tota
                         int32_t* frontface, float* ray_out) {
   int rc = ensure_wavefront(s, fr.capacity);
   if (rc != RT_OK) return rc;
+  rt_scene::Lane& L0 = s->lanes[0];
   cudaStream_t st = s->own_stream;
   const size_t cap = fr.capacity;
   if ((rc = ensure_buf(s->d_dbg, cap * 36)) != RT_OK) return rc;
@@ -672,18 +767,18 @@ static int trace_common(rt_scene* s, const rt_frame& fr, unsigned long long tota
       std::memcpy(&C[4 * i + 2], &sb, 4);
       C[4 * i + 3] = 0.0f;
     }
-    CUDA_TRY(cudaMemcpyAsync(s->paths[0].A, A.data(), (size_t)n * 16, cudaMemcpyHostToDevice, st));
-    CUDA_TRY(cudaMemcpyAsync(s->paths[0].B, B.data(), (size_t)n * 16, cudaMemcpyHostToDevice, st));
-    CUDA_TRY(cudaMemcpyAsync(s->paths[0].C, C.data(), (size_t)n * 16, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(L0.paths[0].A, A.data(), (size_t)n * 16, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(L0.paths[0].B, B.data(), (size_t)n * 16, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(L0.paths[0].C, C.data(), (size_t)n * 16, cudaMemcpyHostToDevice, st));
   }
   rt_frame f2 = fr;
   // single iteration; with supplied rays the control block starts with n_next = n and no new work
-  rt::launch_init(s->ctrl, ray_od ? 0ull : total, st);
-  if (ray_od) CUDA_TRY(cudaMemcpyAsync(&s->ctrl->n_next, &n, 4, cudaMemcpyHostToDevice, st));
-  rt::launch_advance(s->ctrl, f2.capacity, st);
-  if (!ray_od) rt::launch_raygen(f2, s->ctrl, s->paths[0], st);
-  rt::launch_trace(s->dev, f2, s->ctrl, s->paths[0], s->hits, false, s->persistent_blocks, st);
-  rt::launch_surface(s->dev, f2, s->ctrl, s->paths[0], s->hits, dbg, st);
+  rt::launch_init(L0.ctrl, 0ull, ray_od ? 0ull : total, st);
+  if (ray_od) CUDA_TRY(cudaMemcpyAsync(&L0.ctrl->n_next, &n, 4, cudaMemcpyHostToDevice, st));
+  rt::launch_advance(L0.ctrl, f2.capacity, st);
+  if (!ray_od) rt::launch_raygen(f2, L0.ctrl, L0.paths[0], st);
+  rt::launch_trace(s->dev, f2, L0.ctrl, L0.paths[0], L0.hits, false, s->persistent_blocks, st);
+  rt::launch_surface(s->dev, f2, L0.ctrl, L0.paths[0], L0.hits, dbg, st);
   CUDA_TRY(cudaGetLastError());
   std::vector<float> H0((size_t)n * 4), H1((size_t)n * 4), HH((size_t)n * 4);
   std::vector<uint32_t> H2(n);
@@ -692,12 +787,12 @@ static int trace_common(rt_scene* s, const rt_frame& fr, unsigned long long tota
   CUDA_TRY(cudaMemcpyAsync(H0.data(), dbg.S0, (size_t)n * 16, cudaMemcpyDeviceToHost, st));
   CUDA_TRY(cudaMemcpyAsync(H1.data(), dbg.S1, (size_t)n * 16, cudaMemcpyDeviceToHost, st));
   CUDA_TRY(cudaMemcpyAsync(H2.data(), dbg.S2, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
-  CUDA_TRY(cudaMemcpyAsync(HH.data(), s->hits.H, (size_t)n * 16, cudaMemcpyDeviceToHost, st));
-  CUDA_TRY(cudaMemcpyAsync(o.data(), s->hits.obj, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaMemcpyAsync(HH.data(), L0.hits.H, (size_t)n * 16, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaMemcpyAsync(o.data(), L0.hits.obj, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
   if (ray_out) {
     A.resize((size_t)n * 4); B.resize((size_t)n * 4);
-    CUDA_TRY(cudaMemcpyAsync(A.data(), s->paths[0].A, (size_t)n * 16, cudaMemcpyDeviceToHost, st));
-    CUDA_TRY(cudaMemcpyAsync(B.data(), s->paths[0].B, (size_t)n * 16, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(A.data(), L0.paths[0].A, (size_t)n * 16, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(B.data(), L0.paths[0].B, (size_t)n * 16, cudaMemcpyDeviceToHost, st));
   }
   CUDA_TRY(cudaStreamSynchronize(st));
   for (uint32_t i = 0; i < n; ++i) {

@@ -35,6 +35,9 @@ namespace rt {
 #define RT_SMEM_STACK 16   // traversal-stack entries per thread kept in shared memory
 #endif
 #define RT_LOCAL_STACK 48  // overflow entries (local memory; host checks depth <= 62)
+#ifndef RT_STACK_DIST
+#define RT_STACK_DIST 0
+#endif
 #ifndef RT_OCTANT_SORT
 #define RT_OCTANT_SORT 1
 #endif
@@ -160,7 +163,7 @@ struct Best {
   uint32_t prim; // original triangle index inside the mesh
 };
 struct Cnt {
-  uint32_t nodes, tris, inst, prims, rounds;
+  uint32_t nodes, tris, inst, prims, rounds, tlas_nodes;
 };
 
 // reference ordering of candidates: smaller t wins; equal t: earlier object wins (strict '<' in
@@ -240,18 +243,45 @@ struct Trav {
     wd = mk(a.w, b.x, b.y);
   }
 
-  __device__ __forceinline__ void push(uint32_t v) {
+#if RT_STACK_DIST
+  // every entry carries the distance at which the ray enters its box, so that an entry that has fallen behind the
+  // closest hit found since it was pushed is discarded without fetching its children (8-byte entries)
+  __device__ __forceinline__ void push(uint32_t v, float tn = 0.0f) {
+    if (sp < RT_SMEM_STACK)
+      asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(sbase + (uint32_t)sp * (RT_BLOCK * 8u)), "r"(v), "r"(__float_as_uint(tn)) : "memory");
+    else {
+      lstack[2 * (sp - RT_SMEM_STACK)] = v;
+      lstack[2 * (sp - RT_SMEM_STACK) + 1] = __float_as_uint(tn);
+    }
+    ++sp;
+  }
+  __device__ __forceinline__ uint32_t pop(float& tn) {
+    --sp;
+    uint32_t v, w;
+    if (sp < RT_SMEM_STACK)
+      asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v), "=r"(w) : "r"(sbase + (uint32_t)sp * (RT_BLOCK * 8u)) : "memory");
+    else {
+      v = lstack[2 * (sp - RT_SMEM_STACK)];
+      w = lstack[2 * (sp - RT_SMEM_STACK) + 1];
+    }
+    tn = __uint_as_float(w);
+    return v;
+  }
+#else
+  __device__ __forceinline__ void push(uint32_t v, float = 0.0f) {
     if (sp < RT_SMEM_STACK) asm volatile("st.shared.u32 [%0], %1;" ::"r"(sbase + (uint32_t)sp * (RT_BLOCK * 4u)), "r"(v) : "memory");
     else lstack[sp - RT_SMEM_STACK] = v;
     ++sp;
   }
-  __device__ __forceinline__ uint32_t pop() {
+  __device__ __forceinline__ uint32_t pop(float& tn) {
     --sp;
     uint32_t v;
     if (sp < RT_SMEM_STACK) asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(sbase + (uint32_t)sp * (RT_BLOCK * 4u)) : "memory");
     else v = lstack[sp - RT_SMEM_STACK];
+    tn = 0.0f;
     return v;
   }
+#endif
   __device__ __forceinline__ void set_space(f3 no, f3 nd) {
     o = no; d = nd;
     inv = approx_inv(d);
@@ -274,13 +304,17 @@ struct Trav {
   // world-space ray and leaves entry = NONE (the caller pops again).
   __device__ __forceinline__ bool pop_next() {
     if (sp == 0) return false;
-    entry = pop();
+    float tn;
+    entry = pop(tn);
     if (entry == RT_ENTRY_RESTORE) {
       world_ray(o, d);
       load_world_inv();
       in_blas = false;
       entry = RT_ENTRY_NONE;
     }
+#if RT_STACK_DIST
+    else if (tn > best.t) entry = RT_ENTRY_NONE;  // fell behind the closest hit: drop it, the caller pops again
+#endif
     return true;
   }
 };
@@ -292,14 +326,17 @@ __device__ __forceinline__ void trav_interior(const rt_dev_scene& sc, Trav& T) {
   uint32_t e = T.entry;
   const float4* pair = reinterpret_cast<const float4*>(sc.nodes) + (size_t)e * 2u;
   float4 l0 = __ldg(pair), l1 = __ldg(pair + 1), r0 = __ldg(pair + 2), r1 = __ldg(pair + 3);
-  if (COUNT) T.cnt.nodes += 2;
+  if (COUNT) {
+    T.cnt.nodes += 2;
+    if (!T.in_blas) T.cnt.tlas_nodes += 2;
+  }
   float tl, tr;
   bool hl = slab(l0, l1, T.inv, T.oi, T.t_min, T.best.t, tl);
   bool hr = slab(r0, r1, T.inv, T.oi, T.t_min, T.best.t, tr);
   uint32_t el = fbits(l0.w), er = fbits(r0.w);
   if (hl && hr) {
     bool lfirst = tl <= tr;
-    T.push(lfirst ? er : el);
+    T.push(lfirst ? er : el, lfirst ? tr : tl);
     T.entry = lfirst ? el : er;
   } else {
     T.entry = hl ? el : (hr ? er : RT_ENTRY_NONE);
@@ -341,78 +378,80 @@ __device__ __forceinline__ void trav_leaf(const rt_dev_scene& sc, Trav& T) {
     return;
   }
   const f3 wo = T.o, wd = T.d;  // not inside an instance: the current space IS world space
-  int obj = (int)first;
-  uint32_t q = (uint32_t)obj * RT_OBJ_QUADS;
-  float4 h = ldq(sc.objects, q);
-  int kind = (int)fbits(h.x);
-  if (kind == RT_OBJ_MESH) {
-    float4 r0 = ldq(sc.objects, q + 1), r1 = ldq(sc.objects, q + 2), r2 = ldq(sc.objects, q + 3);
-    float4 m7 = ldq(sc.objects, q + 7);
-    if (COUNT) T.cnt.inst += 1;
-    // StaticMesh::intersect_ray, geometry.rs:304: transform_point / transform_vector
-    f3 no = mk(r0.x * wo.x + r0.y * wo.y + r0.z * wo.z + r0.w * 1.0f, r1.x * wo.x + r1.y * wo.y + r1.z * wo.z + r1.w * 1.0f,
-               r2.x * wo.x + r2.y * wo.y + r2.z * wo.z + r2.w * 1.0f);
-    f3 nd = mk(r0.x * wd.x + r0.y * wd.y + r0.z * wd.z + r0.w * 0.0f, r1.x * wd.x + r1.y * wd.y + r1.z * wd.z + r1.w * 0.0f,
-               r2.x * wd.x + r2.y * wd.y + r2.z * wd.z + r2.w * 0.0f);
-    uint32_t root = fbits(m7.x);
-    if (root != RT_ENTRY_NONE) {
-      T.push(RT_ENTRY_RESTORE);
-      T.save_world_inv();
-      T.set_space(no, nd);
-      T.in_blas = true;
-      T.cur_obj = obj;
-      T.entry = root;
+  {
+    const int obj = (int)first;  // one top-level object per TLAS leaf
+    uint32_t q = (uint32_t)obj * RT_OBJ_QUADS;
+    float4 h = ldq(sc.objects, q);
+    int kind = (int)fbits(h.x);
+    if (kind == RT_OBJ_MESH) {  // always alone in its leaf
+      float4 r0 = ldq(sc.objects, q + 1), r1 = ldq(sc.objects, q + 2), r2 = ldq(sc.objects, q + 3);
+      float4 m7 = ldq(sc.objects, q + 7);
+      if (COUNT) T.cnt.inst += 1;
+      // StaticMesh::intersect_ray, geometry.rs:304: transform_point / transform_vector
+      f3 no = mk(r0.x * wo.x + r0.y * wo.y + r0.z * wo.z + r0.w * 1.0f, r1.x * wo.x + r1.y * wo.y + r1.z * wo.z + r1.w * 1.0f,
+                 r2.x * wo.x + r2.y * wo.y + r2.z * wo.z + r2.w * 1.0f);
+      f3 nd = mk(r0.x * wd.x + r0.y * wd.y + r0.z * wd.z + r0.w * 0.0f, r1.x * wd.x + r1.y * wd.y + r1.z * wd.z + r1.w * 0.0f,
+                 r2.x * wd.x + r2.y * wd.y + r2.z * wd.z + r2.w * 0.0f);
+      uint32_t root = fbits(m7.x);
+      if (root != RT_ENTRY_NONE) {
+        T.push(RT_ENTRY_RESTORE);
+        T.save_world_inv();
+        T.set_space(no, nd);
+        T.in_blas = true;
+        T.cur_obj = obj;
+        T.entry = root;
+      }
+      return;
     }
-    return;
-  }
-  if (COUNT) T.cnt.prims += 1;
-  float4 q1 = ldq(sc.objects, q + 1);
-  if (kind == RT_OBJ_SPHERE) {
-    float t;
-    if (sphere_t(mk(q1.x, q1.y, q1.z), q1.w, wo, wd, t_min, t_max, t) && better(t, obj, 0u, best)) {
-      best.t = t; best.obj = obj; best.prim = 0;
-    }
-  } else if (kind == RT_OBJ_TRIANGLE) {
-    // Triangle::intersect_ray, geometry.rs:433-447
-    float4 q2 = ldq(sc.objects, q + 2), q3 = ldq(sc.objects, q + 3);
-    f3 va = mk(q1.x, q1.y, q1.z), e1 = mk(q1.w, q2.x, q2.y), e2 = mk(q2.z, q2.w, q3.x);
-    f3 qv = cross(wd, e2);
-    float g = dot(e1, qv);
-    if (!(fabsf(g) < 0.0001f)) {
-      float f = 1.0f / g;
-      f3 s = wo - va;
-      float u = f * dot(s, qv);
-      if (!(u < 0.0f)) {
-        f3 r = cross(s, e1);
-        float v = f * dot(wd, r);
-        if (!(v < 0.0f || u + v > 1.0f)) {
-          float t = f * dot(e2, r);
-          if (!(t < t_min || t > t_max) && better(t, obj, 0u, best)) {
-            best.t = t; best.obj = obj; best.prim = 0;
+    if (COUNT) T.cnt.prims += 1;
+    float4 q1 = ldq(sc.objects, q + 1);
+    if (kind == RT_OBJ_SPHERE) {
+      float t;
+      if (sphere_t(mk(q1.x, q1.y, q1.z), q1.w, wo, wd, t_min, t_max, t) && better(t, obj, 0u, best)) {
+        best.t = t; best.obj = obj; best.prim = 0;
+      }
+    } else if (kind == RT_OBJ_TRIANGLE) {
+      // Triangle::intersect_ray, geometry.rs:433-447
+      float4 q2 = ldq(sc.objects, q + 2), q3 = ldq(sc.objects, q + 3);
+      f3 va = mk(q1.x, q1.y, q1.z), e1 = mk(q1.w, q2.x, q2.y), e2 = mk(q2.z, q2.w, q3.x);
+      f3 qv = cross(wd, e2);
+      float g = dot(e1, qv);
+      if (!(fabsf(g) < 0.0001f)) {
+        float f = 1.0f / g;
+        f3 s = wo - va;
+        float u = f * dot(s, qv);
+        if (!(u < 0.0f)) {
+          f3 r = cross(s, e1);
+          float v = f * dot(wd, r);
+          if (!(v < 0.0f || u + v > 1.0f)) {
+            float t = f * dot(e2, r);
+            if (!(t < t_min || t > t_max) && better(t, obj, 0u, best)) {
+              best.t = t; best.obj = obj; best.prim = 0;
+            }
           }
         }
       }
-    }
-  } else if (kind == RT_OBJ_VOLUME) {
-    // ConvexVolume::intersect_ray with a Sphere boundary, geometry.rs:505-525
-    float4 q2 = ldq(sc.objects, q + 2);
-    f3 c = mk(q1.x, q1.y, q1.z);
-    float t_entr, t_exit;
-    if (sphere_t(c, q1.w, wo, wd, -CUDART_MAX_NORMAL_F, CUDART_MAX_NORMAL_F, t_entr) &&
-        sphere_t(c, q1.w, wo, wd, t_entr + 0.0001f, CUDART_MAX_NORMAL_F, t_exit) && !(t_exit < t_min || t_entr > t_max)) {
-      float t_start = fmaxf(t_entr, t_min);
-      float t_end = fminf(t_exit, t_max);
-      float dist_in = t_end - t_start;
-      uint32_t vi = fbits(q2.y);
-      float4 kc = T.qC[T.slot];
-      uint32_t pixel = fbits(kc.y), sb = fbits(kc.z);
-      u4 rr = philox4x32_10(pixel, sb & 0xFFFFFFu, sb >> 24, 1u + (vi >> 2), T.k0, T.k1);
-      uint32_t w = (vi & 3u) == 0 ? rr.x : ((vi & 3u) == 1 ? rr.y : ((vi & 3u) == 2 ? rr.z : rr.w));
-      float dist_before = (-1.0f / q2.x) * logf(u01(w));
-      if (dist_before < dist_in) {
-        float t = t_start + dist_before;
-        if (better(t, obj, 0u, best)) {
-          best.t = t; best.obj = obj; best.prim = 0;
+    } else if (kind == RT_OBJ_VOLUME) {
+      // ConvexVolume::intersect_ray with a Sphere boundary, geometry.rs:505-525
+      float4 q2 = ldq(sc.objects, q + 2);
+      f3 c = mk(q1.x, q1.y, q1.z);
+      float t_entr, t_exit;
+      if (sphere_t(c, q1.w, wo, wd, -CUDART_MAX_NORMAL_F, CUDART_MAX_NORMAL_F, t_entr) &&
+          sphere_t(c, q1.w, wo, wd, t_entr + 0.0001f, CUDART_MAX_NORMAL_F, t_exit) && !(t_exit < t_min || t_entr > t_max)) {
+        float t_start = fmaxf(t_entr, t_min);
+        float t_end = fminf(t_exit, t_max);
+        float dist_in = t_end - t_start;
+        uint32_t vi = fbits(q2.y);
+        float4 kc = T.qC[T.slot];
+        uint32_t pixel = fbits(kc.y), sb = fbits(kc.z);
+        u4 rr = philox4x32_10(pixel, sb & 0xFFFFFFu, sb >> 24, 1u + (vi >> 2), T.k0, T.k1);
+        uint32_t w = (vi & 3u) == 0 ? rr.x : ((vi & 3u) == 1 ? rr.y : ((vi & 3u) == 2 ? rr.z : rr.w));
+        float dist_before = (-1.0f / q2.x) * logf(u01(w));
+        if (dist_before < dist_in) {
+          float t = t_start + dist_before;
+          if (better(t, obj, 0u, best)) {
+            best.t = t; best.obj = obj; best.prim = 0;
+          }
         }
       }
     }
@@ -460,7 +499,7 @@ __device__ __forceinline__ void trav_begin(const rt_dev_scene& sc, Trav& T, f3 w
   T.best.obj = -1;
   T.best.prim = 0;
   T.best.u = T.best.v = 0.0f;
-  T.cnt = Cnt{0, 0, 0, 0, 0};
+  T.cnt = Cnt{0, 0, 0, 0, 0, 0};
   T.sp = 0;
   T.in_blas = false;
   T.cur_obj = -1;
@@ -646,14 +685,14 @@ __global__ void __launch_bounds__(RT_BLOCK) k_raygen(rt_frame fr, rt_ctrl* __res
 template <bool COUNT>
 __global__ void __launch_bounds__(RT_BLOCK, RT_EXTEND_MIN_BLOCKS) k_trace(rt_dev_scene sc, rt_frame fr, rt_ctrl* __restrict__ ctrl,
                                                                         rt_paths cur, rt_hits hits) {
-  __shared__ uint32_t sstack[(RT_SMEM_STACK + 6) * RT_BLOCK];
+  __shared__ __align__(8) uint32_t sstack[(RT_SMEM_STACK * (RT_STACK_DIST ? 2 : 1) + 6) * RT_BLOCK];
   const uint32_t n_rays = ctrl->n_rays;
   const uint32_t lane = threadIdx.x & 31u;
   const uint32_t FULL = 0xFFFFFFFFu;
-  uint32_t lstack[RT_LOCAL_STACK];
+  uint32_t lstack[RT_LOCAL_STACK * (RT_STACK_DIST ? 2 : 1)];
   Trav T;
-  T.sbase = (uint32_t)__cvta_generic_to_shared(sstack) + threadIdx.x * 4u;
-  T.wbase = T.sbase + RT_SMEM_STACK * (RT_BLOCK * 4u);
+  T.sbase = (uint32_t)__cvta_generic_to_shared(sstack) + threadIdx.x * (RT_STACK_DIST ? 8u : 4u);
+  T.wbase = (uint32_t)__cvta_generic_to_shared(sstack) + RT_SMEM_STACK * (RT_STACK_DIST ? 2u : 1u) * (RT_BLOCK * 4u) + threadIdx.x * 4u;
   T.lstack = lstack;
   T.t_min = fr.t_min; T.t_max = fr.t_max;
   T.k0 = fr.k0; T.k1 = fr.k1;
@@ -674,6 +713,7 @@ __global__ void __launch_bounds__(RT_BLOCK, RT_EXTEND_MIN_BLOCKS) k_trace(rt_dev
         atomicAdd(&ctrl->counters[1], (unsigned long long)T.cnt.tris);
         atomicAdd(&ctrl->counters[2], (unsigned long long)T.cnt.inst);
         atomicAdd(&ctrl->counters[3], (unsigned long long)T.cnt.prims);
+        atomicAdd(&ctrl->counters[10], (unsigned long long)T.cnt.tlas_nodes);
         // SIMT diagnostic (meaningful with RT_REFILL_MIN == 32, i.e. whole batches retire together): nodes fetched
         // by the lanes of the batch vs 32 x what its slowest lane fetched
         uint32_t m = __activemask();
@@ -1083,8 +1123,8 @@ __global__ void k_resolve(const long long* __restrict__ accum, uint32_t npix, ui
   }
 }
 
-__global__ void k_init_ctrl(rt_ctrl* c, unsigned long long total) {
-  c->cursor = 0;
+__global__ void k_init_ctrl(rt_ctrl* c, unsigned long long begin, unsigned long long total) {
+  c->cursor = begin;
   c->total = total;
   c->n_samples = 0;
   c->n_rays_total = 0;
@@ -1096,7 +1136,7 @@ __global__ void k_init_ctrl(rt_ctrl* c, unsigned long long total) {
   for (int i = 0; i < RT_NUM_CLASSES; ++i) c->class_count[i] = 0;
   c->done = 0;
   c->iterations = 0;
-  for (int i = 0; i < 10; ++i) c->counters[i] = 0;
+  for (int i = 0; i < 12; ++i) c->counters[i] = 0;
 }
 // stats that k_advance cannot see until the iteration has run
 __global__ void k_tally(rt_ctrl* c) {
@@ -1105,7 +1145,9 @@ __global__ void k_tally(rt_ctrl* c) {
 }
 
 // ------------------------------------------------------------------ launchers
-void launch_init(rt_ctrl* ctrl, unsigned long long total, cudaStream_t st) { k_init_ctrl<<<1, 1, 0, st>>>(ctrl, total); }
+void launch_init(rt_ctrl* ctrl, unsigned long long begin, unsigned long long end, cudaStream_t st) {
+  k_init_ctrl<<<1, 1, 0, st>>>(ctrl, begin, end);
+}
 void launch_advance(rt_ctrl* ctrl, uint32_t capacity, cudaStream_t st) {
   k_advance<<<1, 1, 0, st>>>(ctrl, capacity);
   k_tally<<<1, 1, 0, st>>>(ctrl);

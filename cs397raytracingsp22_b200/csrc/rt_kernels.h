@@ -28,7 +28,7 @@ struct rt_debug {
   uint32_t* S2;
 };
 
-void launch_init(rt_ctrl* ctrl, unsigned long long total, cudaStream_t st);
+void launch_init(rt_ctrl* ctrl, unsigned long long begin, unsigned long long end, cudaStream_t st);  // work indices [begin, end)
 void launch_advance(rt_ctrl* ctrl, uint32_t capacity, cudaStream_t st);
 void launch_raygen(const rt_frame& fr, rt_ctrl* ctrl, rt_paths cur, cudaStream_t st);
 void launch_trace(const rt_dev_scene& sc, const rt_frame& fr, rt_ctrl* ctrl, rt_paths cur, rt_hits hits, bool count,

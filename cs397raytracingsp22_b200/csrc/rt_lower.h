@@ -38,6 +38,7 @@ struct HostMesh {
   float root_min[3], root_max[3];
   uint32_t root_entry_local;   // packed entry of the root (local indices)
   uint32_t n_reachable;
+  uint32_t depth = 0;          // longest root-to-leaf path of the BLAS, in nodes
   uint32_t ntris() const { return (uint32_t)(idx.size() / 3); }
 };
 
@@ -60,6 +61,7 @@ struct Lowered {
   uint32_t tlas_root = RT_ENTRY_NONE;
   float tlas_min[3] = {0, 0, 0}, tlas_max[3] = {0, 0, 0};
   uint32_t n_volumes = 0;
+  uint32_t tlas_depth = 0;
   uint64_t bytes() const;
 };
 

@@ -78,8 +78,8 @@ struct rt_ctrl {
   uint32_t done;                   // 1 when cursor==total and nothing is in flight
   uint32_t iterations;
   uint32_t pad_;
-  unsigned long long counters[10]; // nodes, tris, instances, prims, mesh_hits, shade taps, mats, invalid tile slots,
-                                   // normal-map taps (k_extend), -
+  unsigned long long counters[12]; // nodes, tris, instances, prims, mesh_hits, shade taps, mats, invalid tile slots,
+                                   // normal-map taps, warp node slots, TLAS nodes, -
 };
 
 struct rt_frame {

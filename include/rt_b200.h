@@ -115,6 +115,7 @@ typedef struct rt_stats {
   uint64_t shade_launches;    /* k_shade launches that had rays                     */
   /* device counters, filled only with RT_OPT_COUNTERS */
   uint64_t nodes_visited;     /* 32-byte BVH nodes fetched                          */
+  uint64_t tlas_nodes_visited;/* of those, nodes of the top-level BVH               */
   uint64_t tris_tested;       /* 48-byte triangle records fetched                   */
   uint64_t instances_entered; /* 96 bytes of transforms fetched                     */
   uint64_t prims_tested;      /* analytic sphere/triangle/plane/volume records      */
@@ -168,6 +169,17 @@ int rt_add_volume_sphere(rt_scene* s, const float center[3], float radius, float
 /* Lower the scene (reachability mask, binned-SAH BLAS/TLAS, tables) and upload it to
  * CUDA device `device`.  May be called again after more rt_add_* calls. */
 int rt_commit(rt_scene* s, int device);
+/* Host-only half of rt_commit: lower the scene (no CUDA needed) and report what was built. */
+typedef struct rt_lower_info {
+  uint64_t bytes;          /* size of the lowered scene                              */
+  uint32_t nodes;          /* 32-byte BVH nodes, all BLASes + TLAS                   */
+  uint32_t tris;           /* packed (reachable) triangle records                    */
+  uint32_t objects;        /* top-level objects                                      */
+  uint32_t unbounded;      /* objects tested for every ray (planes)                  */
+  uint32_t tlas_depth;     /* longest root-to-leaf path of the TLAS, in nodes        */
+  uint32_t max_blas_depth; /* same for the deepest BLAS                              */
+} rt_lower_info;
+int rt_scene_lower(rt_scene* s, rt_lower_info* info);
 /* Bytes of lowered scene data resident on the device (what rt_commit uploads). */
 uint64_t rt_scene_device_bytes(const rt_scene* s);
 /* Re-upload the already lowered scene from host memory (used to time host->device). */

@@ -29,7 +29,7 @@ def test_struct_layouts_match_the_header():
     assert C.sizeof(_ffi.rt_material_desc) == 40
     assert C.sizeof(_ffi.rt_camera) == 84
     assert C.sizeof(_ffi.rt_render_opts) == 40
-    assert C.sizeof(_ffi.rt_stats) == 15 * 8 + 4 * 8 + 2 * 8
+    assert C.sizeof(_ffi.rt_stats) == 16 * 8 + 4 * 8 + 2 * 8
 
 
 def test_no_gpu_is_a_loud_error_not_a_fallback(rtlib):
@@ -167,3 +167,34 @@ def test_drone_maps_are_deterministic():
     assert all(np.array_equal(x.rgb8, y.rgb8) for x, y in zip(a, b))
     assert [int(x.rgb8.astype(np.int64).sum()) for x in a] == [int(x.rgb8.astype(np.int64).sum()) for x in b]
     assert a[1].rgb8.max() > 0 and (a[1].rgb8 == 0).mean() > 0.5      # emission: mostly black, some seams
+
+
+def test_lowering_on_the_host(small_scenes):
+    """rt_scene_lower is the CPU half of rt_commit: reachability mask, binned/sweep SAH BLASes, TLAS, tables."""
+    b = _ffi.GpuBackend()
+    small_scenes("c4").lower(b)
+    info = b.lower_info()
+    assert info["objects"] == 25 and info["unbounded"] == 1                 # the floor Plane is the only unbounded object
+    assert info["tris"] == (1736 - 51) + 12 + 32512                        # Q3: 51 drone triangles are unreachable
+    assert info["tris"] / 4 <= info["nodes"] <= 2 * info["tris"] + 200
+    assert 3 <= info["tlas_depth"] <= 12 and 10 <= info["max_blas_depth"] <= 40
+    assert info["tlas_depth"] + 1 + info["max_blas_depth"] <= 62            # fits the traversal stack
+    b5 = _ffi.GpuBackend()
+    small_scenes("c5").lower(b5)
+    i5 = b5.lower_info()
+    assert i5["objects"] == 6 * 6 + 3 and i5["tris"] == (1736 - 51) + 240   # shared BLASes: one drone, one teapot
+
+
+def test_degenerate_mesh_still_builds_a_bounded_bvh():
+    """All centroids coincide: SAH cannot split, the builder falls back to median splits (depth = log2 n)."""
+    n = 512
+    pos = np.tile(np.array([[0, 0, 0], [1, 0, 0], [0, 1, 0.5]], np.float32), (n, 1))
+    nrm = np.tile(np.array([[0, 0, 1]], np.float32), (3 * n, 1))
+    uv = np.tile(np.array([[0, 0], [1, 0], [0, 1]], np.float32), (n, 1))
+    idx = np.arange(3 * n, dtype=np.uint32).reshape(n, 3)
+    b = _ffi.GpuBackend()
+    m = b.add_mesh(pos, nrm, uv, idx)
+    b.add_instance(m, np.eye(4, dtype=np.float32).reshape(-1), np.eye(4, dtype=np.float32).reshape(-1),
+                   b.add_material(_ffi.RT_MAT_LAMBERTIAN), [-1] * 5)
+    info = b.lower_info()
+    assert info["tris"] == n and info["max_blas_depth"] <= 10

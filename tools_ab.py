@@ -21,7 +21,7 @@ for lib in libs:
             d = json.loads(r.stdout.strip().splitlines()[-1])
             rf = d["roofline"]
             print(f"{os.path.basename(lib):20s} {es:28s} {d['value']:8.1f} Msamples/s {d['rays_per_sec_M']:8.1f} Mrays/s  extend {rf['ms_per_launch']*1e3:6.1f} us "
-                  f"({rf['share_of_step']:.3f}) shade {rf['shade_share_of_step']:.3f} nodes/ray {rf['nodes_per_ray']:.2f} tris/ray {rf['tris_per_ray']:.2f} "
+                  f"({rf['share_of_step']:.3f}) shade {rf['shade_share_of_step']:.3f} nodes/ray {rf['nodes_per_ray']:.2f} (tlas {rf.get('tlas_nodes_per_ray',0):.2f}) tris/ray {rf['tris_per_ray']:.2f} "
                   f"simt {rf.get('traversal_simt_efficiency', 0):.3f}", flush=True)
         except Exception as e:
             print(lib, es, "FAILED", e, r.stderr[-400:], flush=True)
