@@ -347,7 +347,7 @@ int run_wavefront(rt_scene* s, const rt_frame& fr_in, unsigned long long total, 
           CUDA_TRY(cudaEventRecord(e2, st));
           ++R.timed_iters;
         }
-        R.launches += 6; ++R.ext; ++R.shd; ++R.it;
+        R.launches += 5; ++R.ext; ++R.shd; ++R.it;
       }
     // poll each lane: copy the done flag written by k_advance, two chunks deep
     for (int li = 0; li < nlanes; ++li) {

@@ -639,6 +639,8 @@ __global__ void k_advance(rt_ctrl* c, uint32_t capacity) {
   for (int i = 0; i < RT_NUM_CLASSES; ++i) c->class_count[i] = 0;
   if (n_cont + n_new == 0) c->done = 1;
   else c->iterations += 1;
+  c->n_rays_total += n_cont + n_new;
+  c->n_samples += n_new;
 }
 
 // ------------------------------------------------------------------ k_raygen
@@ -770,20 +772,25 @@ __global__ void __launch_bounds__(RT_BLOCK, RT_EXTEND_MIN_BLOCKS) k_trace(rt_dev
 // ------------------------------------------------------------------ k_sort
 // material-sorted shade queues: warp match groups -> per-warp counts -> one atomic per class per
 // block -> each hit ray's slot index lands in the queue of its material class
-__global__ void __launch_bounds__(RT_BLOCK) k_sort(rt_dev_scene sc, rt_frame fr, rt_ctrl* __restrict__ ctrl,
+#ifndef RT_SORT_BLOCK
+#define RT_SORT_BLOCK 512
+#endif
+#define RT_SORT_WARPS (RT_SORT_BLOCK / 32)
+__global__ void __launch_bounds__(RT_SORT_BLOCK) k_sort(rt_dev_scene sc, rt_frame fr, rt_ctrl* __restrict__ ctrl,
                                                    const int32_t* __restrict__ hit_obj, uint32_t* __restrict__ queues) {
-  __shared__ uint32_t s_wcount[RT_WARPS][RT_NUM_CLASSES];
+  __shared__ uint32_t s_wcount[RT_SORT_WARPS][RT_NUM_CLASSES];
   __shared__ uint32_t s_base[RT_NUM_CLASSES];
   const uint32_t n_rays = ctrl->n_rays;
-  const uint32_t i = blockIdx.x * RT_BLOCK + threadIdx.x;
-  if (blockIdx.x * RT_BLOCK >= n_rays) return;
+  const uint32_t i = blockIdx.x * RT_SORT_BLOCK + threadIdx.x;
+  if (blockIdx.x * RT_SORT_BLOCK >= n_rays) return;
   const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
   int cls = -1;
   if (i < n_rays) {
     int obj = hit_obj[i];
     if (obj >= 0) cls = (int)fbits(ldq(sc.objects, (uint32_t)obj * RT_OBJ_QUADS).z);
   }
-  if (threadIdx.x < RT_WARPS * RT_NUM_CLASSES) (&s_wcount[0][0])[threadIdx.x] = 0;
+  if (threadIdx.x < RT_SORT_WARPS * RT_NUM_CLASSES) (&s_wcount[0][0])[threadIdx.x] = 0;
+  static_assert(RT_SORT_WARPS * RT_NUM_CLASSES <= RT_SORT_BLOCK, "zero-fill covers the counters");
   __syncthreads();
   uint32_t peers = __match_any_sync(0xFFFFFFFFu, cls);
   uint32_t rank = __popc(peers & ((1u << lane) - 1u));
@@ -792,7 +799,7 @@ __global__ void __launch_bounds__(RT_BLOCK) k_sort(rt_dev_scene sc, rt_frame fr,
   if (threadIdx.x < RT_NUM_CLASSES) {
     uint32_t total = 0;
 #pragma unroll
-    for (int w = 0; w < RT_WARPS; ++w) {
+    for (int w = 0; w < RT_SORT_WARPS; ++w) {
       uint32_t c = s_wcount[w][threadIdx.x];
       s_wcount[w][threadIdx.x] = total;  // exclusive prefix over warps
       total += c;
@@ -887,8 +894,13 @@ __device__ __forceinline__ void accum_add(long long* accum, uint32_t pixel, f3 c
 }
 
 // ------------------------------------------------------------------ k_shade
+// k_shade is latency bound on its gathers: 10 resident blocks (48 registers, ~100 B of spills) beat 7 blocks
+// (72 registers, no spills) by 1 % on C4 and 7-10 % on the closed scenes C1 / C3 where shading dominates
+#ifndef RT_SHADE_MIN_BLOCKS
+#define RT_SHADE_MIN_BLOCKS 10
+#endif
 template <bool COUNT>
-__global__ void __launch_bounds__(RT_BLOCK) k_shade(rt_dev_scene sc, rt_frame fr, rt_ctrl* __restrict__ ctrl,
+__global__ void __launch_bounds__(RT_BLOCK, RT_SHADE_MIN_BLOCKS) k_shade(rt_dev_scene sc, rt_frame fr, rt_ctrl* __restrict__ ctrl,
                                                     rt_paths cur, rt_paths nxt, rt_hits hits,
                                                     const uint32_t* __restrict__ queues, long long* __restrict__ accum) {
 #if RT_OCTANT_SORT
@@ -1138,19 +1150,12 @@ __global__ void k_init_ctrl(rt_ctrl* c, unsigned long long begin, unsigned long 
   c->iterations = 0;
   for (int i = 0; i < 12; ++i) c->counters[i] = 0;
 }
-// stats that k_advance cannot see until the iteration has run
-__global__ void k_tally(rt_ctrl* c) {
-  c->n_rays_total += c->n_rays;
-  c->n_samples += c->n_rays - c->n_cont;
-}
-
 // ------------------------------------------------------------------ launchers
 void launch_init(rt_ctrl* ctrl, unsigned long long begin, unsigned long long end, cudaStream_t st) {
   k_init_ctrl<<<1, 1, 0, st>>>(ctrl, begin, end);
 }
 void launch_advance(rt_ctrl* ctrl, uint32_t capacity, cudaStream_t st) {
   k_advance<<<1, 1, 0, st>>>(ctrl, capacity);
-  k_tally<<<1, 1, 0, st>>>(ctrl);
 }
 int trace_blocks_per_sm() {
   int n = 0;
@@ -1168,7 +1173,7 @@ void launch_trace(const rt_dev_scene& sc, const rt_frame& fr, rt_ctrl* ctrl, rt_
   else k_trace<false><<<grid, RT_BLOCK, 0, st>>>(sc, fr, ctrl, cur, hits);
 }
 void launch_sort(const rt_dev_scene& sc, const rt_frame& fr, rt_ctrl* ctrl, rt_hits hits, uint32_t* queues, cudaStream_t st) {
-  k_sort<<<(fr.capacity + RT_BLOCK - 1) / RT_BLOCK, RT_BLOCK, 0, st>>>(sc, fr, ctrl, hits.obj, queues);
+  k_sort<<<(fr.capacity + RT_SORT_BLOCK - 1) / RT_SORT_BLOCK, RT_SORT_BLOCK, 0, st>>>(sc, fr, ctrl, hits.obj, queues);
 }
 void launch_surface(const rt_dev_scene& sc, const rt_frame& fr, rt_ctrl* ctrl, rt_paths cur, rt_hits hits, rt_debug dbg,
                     cudaStream_t st) {
