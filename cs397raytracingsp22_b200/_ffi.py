@@ -64,7 +64,8 @@ class rt_stats(C.Structure):
 
 class rt_lower_info(C.Structure):
     _fields_ = [("bytes", C.c_uint64), ("nodes", C.c_uint32), ("tris", C.c_uint32), ("objects", C.c_uint32),
-                ("unbounded", C.c_uint32), ("tlas_depth", C.c_uint32), ("max_blas_depth", C.c_uint32)]
+                ("unbounded", C.c_uint32), ("tlas_depth", C.c_uint32), ("max_blas_depth", C.c_uint32),
+                ("guard_boxes", C.c_uint32), ("guarded_tris", C.c_uint32)]
 
 
 class rt_obj_mesh(C.Structure):

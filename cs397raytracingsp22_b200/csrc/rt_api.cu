@@ -51,7 +51,7 @@ struct rt_scene {
   bool lowered = false;
   bool committed = false;
   int device = -1;
-  DevBuf d_nodes, d_tris, d_shade, d_objects, d_mats, d_textures, d_texels, d_planes;
+  DevBuf d_nodes, d_tris, d_shade, d_objects, d_mats, d_textures, d_texels, d_planes, d_guards, d_guard_list;
   rt_dev_scene dev{};
 
   // wavefront state: one or more independent "lanes" (ray queues + control block + stream).  Several lanes let
@@ -461,7 +461,7 @@ void rt_scene_destroy(rt_scene* s) {
   if (s->device >= 0 && cudaSetDevice(s->device) == cudaSuccess) {
     free_wavefront(s);
     free_buf(s->d_nodes); free_buf(s->d_tris); free_buf(s->d_shade); free_buf(s->d_objects);
-    free_buf(s->d_mats); free_buf(s->d_textures); free_buf(s->d_texels); free_buf(s->d_planes);
+    free_buf(s->d_mats); free_buf(s->d_textures); free_buf(s->d_texels); free_buf(s->d_planes); free_buf(s->d_guards); free_buf(s->d_guard_list);
     free_buf(s->d_accum); free_buf(s->d_linear); free_buf(s->d_rgb8); free_buf(s->d_dbg);
     for (auto& L : s->lanes) {
       if (L.ctrl) cudaFree(L.ctrl);
@@ -598,10 +598,12 @@ int rt_scene_upload(rt_scene* s) {
   if ((rc = upload(s->d_textures, L.textures.data(), L.textures.size() * 16, st)) != RT_OK) return rc;
   if ((rc = upload(s->d_texels, L.texels.data(), L.texels.size() * 4, st)) != RT_OK) return rc;
   if ((rc = upload(s->d_planes, L.planes.data(), L.planes.size() * 4, st)) != RT_OK) return rc;
+  if ((rc = upload(s->d_guards, L.guards.data(), L.guards.size() * 16, st)) != RT_OK) return rc;
+  if ((rc = upload(s->d_guard_list, L.guard_list.data(), L.guard_list.size() * 4, st)) != RT_OK) return rc;
   CUDA_TRY(cudaStreamSynchronize(st));
   rt_dev_scene& d = s->dev;
   d.nodes = s->d_nodes.p; d.tris = s->d_tris.p; d.shade = s->d_shade.p; d.objects = s->d_objects.p;
-  d.mats = s->d_mats.p; d.textures = s->d_textures.p; d.texels = s->d_texels.p; d.planes = s->d_planes.p;
+  d.mats = s->d_mats.p; d.textures = s->d_textures.p; d.texels = s->d_texels.p; d.planes = s->d_planes.p; d.guards = s->d_guards.p; d.guard_list = s->d_guard_list.p;
   d.tlas_root = L.tlas_root;
   d.n_planes = (L.planes.size() == 1 && L.planes[0] < 0) ? 0u : (uint32_t)L.planes.size();
   d.n_objects = (uint32_t)s->objects.size();
@@ -633,6 +635,12 @@ int rt_scene_lower(rt_scene* s, rt_lower_info* info) {
     info->objects = (uint32_t)s->objects.size();
     info->unbounded = (L.planes.size() == 1 && L.planes[0] < 0) ? 0u : (uint32_t)L.planes.size();
     info->tlas_depth = L.tlas_depth;
+    info->guard_boxes = 0;
+    info->guarded_tris = 0;
+    for (const auto& m : s->meshes) {
+      info->guard_boxes += (uint32_t)(m.guards.size() / 2);
+      for (size_t q = 0; q < m.tris.size(); q += RT_TRI_QUADS) info->guarded_tris += m.tris[q + 2].u[3] ? 1u : 0u;
+    }
   }
   return RT_OK;
 }

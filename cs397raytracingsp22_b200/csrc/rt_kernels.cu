@@ -319,6 +319,37 @@ struct Trav {
   }
 };
 
+// The reference's AABB::intersect_ray (geometry.rs:52-68), exactly: strict, IEEE division, its own min/max order.
+// Used only for GUARD boxes: thin interior boxes of the reference's index-order tree, which that test rejects for
+// rays whose origin is far enough away that (min - o) == (max - o) in f32.  A triangle below such a box is a hit
+// for the reference only if every guard above it lets the ray in (t_max un-narrowed).
+__device__ __noinline__ bool guards_pass(const rt_dev_scene& sc, uint32_t first, uint32_t count, f3 o, f3 d, float t_min,
+                                         float t_max) {
+  const uint32_t* list = reinterpret_cast<const uint32_t*>(sc.guard_list);
+  const float oo[3] = {o.x, o.y, o.z}, dd[3] = {d.x, d.y, d.z};
+  for (uint32_t k = 0; k < count; ++k) {
+    uint32_t g = __ldg(list + first + k);
+    float4 lo = ldq(sc.guards, g * 2u), hi = ldq(sc.guards, g * 2u + 1u);
+    const float mn[3] = {lo.x, lo.y, lo.z}, mx[3] = {hi.x, hi.y, hi.z};
+    float tmin = t_min, tmax = t_max;
+#pragma unroll
+    for (int axis = 0; axis < 3; ++axis) {
+      float inv_d = 1.0f / dd[axis];
+      float t0 = (mn[axis] - oo[axis]) * inv_d;
+      float t1 = (mx[axis] - oo[axis]) * inv_d;
+      if (inv_d < 0.0f) {
+        float tmp = t0;
+        t0 = t1;
+        t1 = tmp;
+      }
+      tmin = fmaxf(t0, tmin);
+      tmax = fminf(t1, tmax);
+      if (tmax <= tmin) return false;
+    }
+  }
+  return true;
+}
+
 // interior node: fetch the 64-byte child pair with four 128-bit read-only loads, test both boxes,
 // continue with the nearer child and push the other
 template <bool COUNT>
@@ -371,6 +402,7 @@ __device__ __forceinline__ void trav_leaf(const rt_dev_scene& sc, Trav& T) {
       float t = f * dot(e2, r);
       if (t < t_min || t > t_max) continue;
       uint32_t id = fbits(a2.y);
+      if (fbits(a2.w) && !guards_pass(sc, fbits(a2.z), fbits(a2.w), o, d, t_min, t_max)) continue;
       if (better(t, T.cur_obj, id, best)) {
         best.t = t; best.u = u; best.v = v; best.obj = T.cur_obj; best.prim = id;
       }

@@ -22,8 +22,8 @@ static inline float fmin3(float a, float b, float c) { return std::fmin(a, std::
 static inline float fmax3(float a, float b, float c) { return std::fmax(a, std::fmax(b, c)); }
 
 uint64_t Lowered::bytes() const {
-  return (nodes.size() + tris.size() + shade.size() + objects.size() + mats.size() + textures.size()) * 16ull +
-         texels.size() * 4ull + planes.size() * 4ull;
+  return (nodes.size() + tris.size() + shade.size() + objects.size() + mats.size() + textures.size() + guards.size()) * 16ull +
+         texels.size() * 4ull + planes.size() * 4ull + guard_list.size() * 4ull;
 }
 
 // ------------------------------------------------------------------ reachability (Q3)
@@ -35,7 +35,17 @@ namespace {
 struct Box3 {
   float mn[3], mx[3];
 };
-Box3 reach_rec(const float* pos, const uint32_t* idx, uint32_t start, uint32_t end, bool dead, uint8_t* mask) {
+struct GuardRange {
+  Box3 box;
+  uint32_t start, end;  // triangles below the thin interior node
+};
+// An interior box that is thin but not flat is rejected by the same strict test only for rays whose origin is so far
+// away that (min - o) == (max - o) in f32 - ray dependent, so it cannot go into the static mask.  Such boxes are
+// recorded as GUARDS: the kernel re-runs the reference's slab test on them (exactly) before it accepts a hit on a
+// triangle below.  Threshold: thickness below 2^-10 of the largest coordinate; a guard that passes costs nothing
+// but time, so over-flagging is harmless.
+Box3 reach_rec(const float* pos, const uint32_t* idx, uint32_t start, uint32_t end, uint8_t* mask,
+               std::vector<GuardRange>* guards) {
   Box3 b;
   if (end - start == 1) {
     const float* a = pos + 3 * (size_t)idx[3 * start];
@@ -45,27 +55,34 @@ Box3 reach_rec(const float* pos, const uint32_t* idx, uint32_t start, uint32_t e
       b.mn[k] = fmin3(a[k], p[k], c[k]);
       b.mx[k] = fmax3(a[k], p[k], c[k]);
     }
-    mask[start] = dead ? 0 : 1;
+    mask[start] = 1;
     return b;
   }
   uint32_t mid = start + (end - start) / 2;
-  // boxes first (bottom-up), then decide flatness; children inherit `dead` afterwards
-  Box3 l = reach_rec(pos, idx, start, mid, dead, mask);
-  Box3 r = reach_rec(pos, idx, mid, end, dead, mask);
+  Box3 l = reach_rec(pos, idx, start, mid, mask, guards);
+  Box3 r = reach_rec(pos, idx, mid, end, mask, guards);
   for (int k = 0; k < 3; ++k) {
     b.mn[k] = std::fmin(l.mn[k], r.mn[k]);
     b.mx[k] = std::fmax(l.mx[k], r.mx[k]);
   }
   bool flat = b.mn[0] == b.mx[0] || b.mn[1] == b.mx[1] || b.mn[2] == b.mx[2];
-  if (flat && !dead)
+  if (flat) {
     for (uint32_t t = start; t < end; ++t) mask[t] = 0;
+  } else if (guards) {
+    float amax = 0.0f, thin = FLT_MAX;
+    for (int k = 0; k < 3; ++k) {
+      amax = std::max(amax, std::max(std::fabs(b.mn[k]), std::fabs(b.mx[k])));
+      thin = std::min(thin, b.mx[k] - b.mn[k]);
+    }
+    if (thin < amax * (1.0f / 1024.0f)) guards->push_back(GuardRange{b, start, end});
+  }
   return b;
 }
 }  // namespace
 
 void mesh_reachability(const float* pos, const uint32_t* idx, uint32_t ntris, uint8_t* mask) {
   if (ntris == 0) return;
-  reach_rec(pos, idx, 0, ntris, false, mask);
+  reach_rec(pos, idx, 0, ntris, mask, nullptr);
 }
 
 // ------------------------------------------------------------------ binned SAH BVH2
@@ -340,7 +357,36 @@ void nodes_to_quads(const std::vector<BNode>& nodes, float pad, std::vector<Quad
 void build_mesh(HostMesh& m) {
   const uint32_t nt = m.ntris();
   m.reach.assign(nt, 1);
-  mesh_reachability(m.pos.data(), m.idx.data(), nt, m.reach.data());
+  std::vector<GuardRange> granges;
+  if (nt) reach_rec(m.pos.data(), m.idx.data(), 0, nt, m.reach.data(), &granges);
+  // per-triangle guard lists: every thin interior box above a reachable triangle, outermost first
+  // (reach_rec emits children before parents, so walk the ranges backwards)
+  std::vector<std::vector<uint32_t>> tri_guards(nt);
+  m.guards.clear();
+  for (size_t gi = granges.size(); gi-- > 0;) {
+    const GuardRange& g = granges[gi];
+    bool any = false;
+    for (uint32_t t = g.start; t < g.end; ++t) any = any || m.reach[t];
+    if (!any) continue;
+    uint32_t id = (uint32_t)(m.guards.size() / 2);
+    Quad lo{}, hi{};
+    for (int k = 0; k < 3; ++k) {
+      lo.f[k] = g.box.mn[k];
+      hi.f[k] = g.box.mx[k];
+    }
+    m.guards.push_back(lo);
+    m.guards.push_back(hi);
+    for (uint32_t t = g.start; t < g.end; ++t)
+      if (m.reach[t]) tri_guards[t].push_back(id);
+  }
+  // flatten: guard_list holds, per triangle, the indices of its guard boxes
+  m.guard_list.clear();
+  std::vector<uint32_t> g_first(nt, 0), g_count(nt, 0);
+  for (uint32_t t = 0; t < nt; ++t) {
+    g_first[t] = (uint32_t)m.guard_list.size();
+    g_count[t] = (uint32_t)tri_guards[t].size();
+    m.guard_list.insert(m.guard_list.end(), tri_guards[t].begin(), tri_guards[t].end());
+  }
 
   // shading records, original order (geometry.rs:230-250,350-363)
   m.shade.assign((size_t)nt * RT_SHADE_QUADS, Quad{});
@@ -402,7 +448,8 @@ void build_mesh(HostMesh& m) {
     q[1].f[2] = pc[0] - pa[0]; q[1].f[3] = pc[1] - pa[1];
     q[2].f[0] = pc[2] - pa[2];
     q[2].u[1] = t;
-    q[2].u[2] = 0; q[2].u[3] = 0;
+    q[2].u[2] = g_first[t];   // guard list (rebased when the BLASes are concatenated)
+    q[2].u[3] = g_count[t];
   }
 }
 
@@ -451,7 +498,14 @@ int lower_scene(const std::vector<HostTexture>& textures, const std::vector<rt_m
       uint32_t count = L.nodes[q + 1].u[3];
       L.nodes[q].u[3] += count ? tri_base[mi] : node_base[mi];
     }
+    // guards: boxes and per-triangle index lists, rebased to the global arrays
+    uint32_t guard_base = (uint32_t)(L.guards.size() / 2), glist_base = (uint32_t)L.guard_list.size();
+    L.guards.insert(L.guards.end(), m.guards.begin(), m.guards.end());
+    for (uint32_t g : m.guard_list) L.guard_list.push_back(g + guard_base);
+    size_t t0 = L.tris.size();
     L.tris.insert(L.tris.end(), m.tris.begin(), m.tris.end());
+    for (size_t q = t0; q < L.tris.size(); q += RT_TRI_QUADS)
+      if (L.tris[q + 2].u[3]) L.tris[q + 2].u[2] += glist_base;
     L.shade.insert(L.shade.end(), m.shade.begin(), m.shade.end());
     if ((L.tris.size() / RT_TRI_QUADS) >= (1u << 27)) {
       err = "too many triangles";
@@ -623,6 +677,8 @@ int lower_scene(const std::vector<HostTexture>& textures, const std::vector<rt_m
   if (L.mats.empty()) L.mats.assign(RT_MAT_QUADS, Quad{});
   if (L.textures.empty()) L.textures.push_back(Quad{});
   if (L.tris.empty()) L.tris.assign(RT_TRI_QUADS, Quad{});
+  if (L.guards.empty()) L.guards.assign(2, Quad{});
+  if (L.guard_list.empty()) L.guard_list.push_back(0);
   if (L.shade.empty()) L.shade.assign(RT_SHADE_QUADS, Quad{});
 
   // TLAS: one object per leaf, the leaf's link holds the object index directly.  (Measured: leaves of 2-8 analytic

@@ -35,6 +35,8 @@ struct HostMesh {
   std::vector<Quad> nodes;     // 2 per node
   std::vector<Quad> tris;      // 3 per packed triangle, leaf order
   std::vector<Quad> shade;     // 5 per ORIGINAL triangle
+  std::vector<Quad> guards;    // 2 per guard box (thin interior boxes of the reference tree, see rt_lower.cpp)
+  std::vector<uint32_t> guard_list;  // per-triangle lists of guard indices
   float root_min[3], root_max[3];
   uint32_t root_entry_local;   // packed entry of the root (local indices)
   uint32_t n_reachable;
@@ -58,6 +60,8 @@ struct Lowered {
   std::vector<Quad> textures;
   std::vector<uint32_t> texels;
   std::vector<int32_t> planes;
+  std::vector<Quad> guards;
+  std::vector<uint32_t> guard_list;
   uint32_t tlas_root = RT_ENTRY_NONE;
   float tlas_min[3] = {0, 0, 0}, tlas_max[3] = {0, 0, 0};
   uint32_t n_volumes = 0;

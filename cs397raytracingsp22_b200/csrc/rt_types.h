@@ -9,7 +9,9 @@
 //             count>0 : leaf, link = RT_LEAF_FLAG | first << 4 | count;
 //                       BLAS leaf => `count` triangle records from `first`,
 //                       TLAS leaf => count==1, first = top-level object index
-//   tris    : 3 quads (48 B) per triangle, leaf order: (v0.xyz,e1.x)(e1.yz,e2.xy)(e2.z,id,_,_)
+//   tris    : 3 quads (48 B) per triangle, leaf order: (v0.xyz,e1.x)(e1.yz,e2.xy)(e2.z,id,guard first,guard count)
+//   guards  : 2 quads per guard box + a uint32 index list: thin interior boxes of the REFERENCE's tree whose strict
+//             slab test must be replayed before a hit below them is accepted (rare; see rt_lower.cpp)
 //   shade   : 5 quads (80 B) per triangle, ORIGINAL order: na nb nc uva uvb uvc tangent
 //   objects : 10 quads (160 B) per top-level object, insertion order (tie-breaking!)
 //   mats    : 2 quads (32 B) per material
@@ -54,6 +56,8 @@ struct rt_dev_scene {
   const void* textures;  // uint4*  (texel offset, w, h, 0)
   const void* texels;    // uint32_t* RGBA8
   const void* planes;    // int32_t* indices of unbounded objects (always tested)
+  const void* guards;    // float4* guard boxes (min, max)
+  const void* guard_list;// uint32_t* per-triangle guard indices
   uint32_t tlas_root;    // packed entry of the TLAS root, RT_ENTRY_NONE when there is none
   uint32_t n_planes;
   uint32_t n_objects;

@@ -178,6 +178,8 @@ typedef struct rt_lower_info {
   uint32_t unbounded;      /* objects tested for every ray (planes)                  */
   uint32_t tlas_depth;     /* longest root-to-leaf path of the TLAS, in nodes        */
   uint32_t max_blas_depth; /* same for the deepest BLAS                              */
+  uint32_t guard_boxes;    /* thin interior boxes of the reference tree kept as guards */
+  uint32_t guarded_tris;   /* triangles that have at least one guard                  */
 } rt_lower_info;
 int rt_scene_lower(rt_scene* s, rt_lower_info* info);
 /* Bytes of lowered scene data resident on the device (what rt_commit uploads). */

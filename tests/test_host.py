@@ -179,6 +179,7 @@ def test_lowering_on_the_host(small_scenes):
     assert info["tris"] / 4 <= info["nodes"] <= 2 * info["tris"] + 200
     assert 3 <= info["tlas_depth"] <= 12 and 10 <= info["max_blas_depth"] <= 40
     assert info["tlas_depth"] + 1 + info["max_blas_depth"] <= 62            # fits the traversal stack
+    assert 0 < info["guard_boxes"] < 200 and 0 < info["guarded_tris"] < 600  # drone.obj's nearly-flat disc caps
     b5 = _ffi.GpuBackend()
     small_scenes("c5").lower(b5)
     i5 = b5.lower_info()

@@ -193,8 +193,9 @@ def test_tree_vs_brute_force_on_tiny_instances(small_scenes):
     """Where the static mask of Q3 stops being the whole story.  C5 scales drone.obj by 6e-4, so object-space ray
     origins are ~1e4 units out and (min - o) == (max - o) in f32 for the mesh's 2-ulp-thick interior boxes
     (x = 498.367676 vs 498.367737): the reference's strict slab test then rejects those nodes for THAT ray.  The
-    effect is ray dependent, bounded, and one-sided (brute force only ever finds a closer hit); DESIGN.md §parity
-    states it.  The CUDA path follows the brute-force semantics."""
+    effect is ray dependent, bounded, and one-sided (brute force only ever finds a closer hit).  The CUDA path keeps
+    such boxes as GUARDS and replays the reference's test on them, so it follows the reference tree here too
+    (tests/test_gpu_parity.py::test_guards_follow_the_reference_tree_where_brute_force_does_not)."""
     sc = small_scenes("c5")
     b = O.lower_to_oracle(sc)
     cam = sc.camera.to_c()
