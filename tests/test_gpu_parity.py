@@ -330,3 +330,77 @@ def test_two_ranks_render_and_reduce_to_the_single_gpu_frame(gpu):
         p.join(timeout=60)
         assert p.exitcode == 0
     assert ok, "sum of the two ranks' accumulators differs from the single-GPU accumulator"
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# BASELINE.json's full sizes, through properties that do not need the CPU to render the frame
+# ---------------------------------------------------------------------------------------------------------------
+def test_full_size_c1_properties(gpu):
+    """C1 at its full BASELINE size (512x512, 64 spp, depth 8 = 16.8 M paths, 134 M rays): closed scene => every path
+    runs to path_depth; the frame is bit-reproducible; three sample-range shards and four tile shards sum to it; the
+    primary hits of one sample agree with the oracle on every pixel; mean radiance agrees with a 64x64 oracle render of
+    the same scene to Monte-Carlo accuracy."""
+    import torch
+    from cs397raytracingsp22_b200 import scenes
+    sc = scenes.make_scene("c1")
+    g, o = _both(sc)
+    cam = sc.camera.to_c()
+    w, h, spp, depth = cam.screen_width, cam.screen_height, cam.aa_sample_count, cam.path_depth
+    assert (w, h, spp, depth) == (512, 512, 64, 8)
+    dev = torch.device("cuda", 0)
+
+    def run(opts_list):
+        acc = D.new_accum(w, h, dev)
+        stats = [D.render_shard(g, cam, op, acc) for op in opts_list]
+        torch.cuda.synchronize()
+        return acc, stats
+
+    full, st = run([D.shard_opts(0, 1, SEED, "all")])
+    assert st[0].samples == w * h * spp
+    assert 0.999 * st[0].samples * depth <= st[0].rays <= st[0].samples * depth
+    again, _ = run([D.shard_opts(0, 1, SEED, "all")])
+    assert torch.equal(full, again)
+    by_samples, _ = run([D.shard_opts(r, 3, SEED, "samples") for r in range(3)])
+    assert torch.equal(full, by_samples)
+    by_tiles, sts = run([D.shard_opts(r, 4, SEED, "tiles", tile=48) for r in range(4)])     # 48 does not divide 512
+    assert torch.equal(full, by_tiles)
+    assert sum(s.samples for s in sts) == w * h * spp
+    # a checksum of checksums: per-row sums of the integer accumulator add up to the total, channel by channel
+    a = full.view(h, w, 4)
+    assert torch.equal(a.sum(dim=1).sum(dim=0), a.sum(dim=(0, 1)))
+    assert int(a[..., 3].abs().sum()) == 0                                                   # no NaN samples
+    prim_g = g.trace_primary(cam, SEED, 5)
+    prim_o = o.trace_primary(cam, SEED, 5, mode=O.MODE_REF_TREE)
+    assert np.array_equal(prim_g["ray"], prim_o["ray"])
+    assert np.array_equal(prim_g["obj"], prim_o["obj"]) and np.array_equal(prim_g["t"], prim_o["t"])
+    lin, _ = D.resolve(g, cam, full, spp)
+    small = scenes.make_scene("c1", width=64, height=64, spp=256)
+    lin_o, _, _ = O.lower_to_oracle(small).render(small.camera.to_c(), seed=3)
+    assert abs(float(lin.mean()) - float(lin_o.mean())) < 0.02 * float(lin_o.mean())
+
+
+def test_full_resolution_c4_properties(gpu):
+    """C4 at its full resolution and depth (1920x1080, 2048^2 maps, depth 10) with 16 of the 1024 sample indices:
+    33 M paths.  Sample-range shards sum to the frame bit for bit; primary hits of one sample index agree with the
+    oracle on every one of the 2 M pixels; the ray count stays within the reference's (Q: zero-throughput paths)."""
+    import torch
+    from cs397raytracingsp22_b200 import scenes
+    sc = scenes.make_scene("c4")
+    g, o = _both(sc)
+    cam = sc.camera.to_c()
+    w, h = cam.screen_width, cam.screen_height
+    assert (w, h, cam.aa_sample_count, cam.path_depth) == (1920, 1080, 1024, 10)
+    dev = torch.device("cuda", 0)
+    lo, hi = 500, 516
+    full = D.new_accum(w, h, dev)
+    st = D.render_shard(g, cam, D.shard_opts(0, 1, SEED, "all", sample_begin=lo, sample_end=hi), full)
+    parts = D.new_accum(w, h, dev)
+    for r in range(4):
+        D.render_shard(g, cam, D.shard_opts(r, 4, SEED, "samples", sample_begin=lo, sample_end=hi), parts)
+    torch.cuda.synchronize()
+    assert st.samples == w * h * (hi - lo) and st.samples <= st.rays <= st.samples * cam.path_depth
+    assert torch.equal(full, parts)
+    a = g.trace_primary(cam, SEED, 777)
+    b = o.trace_primary(cam, SEED, 777, mode=O.MODE_REF_TREE)
+    assert np.array_equal(a["ray"], b["ray"])
+    _assert_hits_match(a, b, "c4 full resolution", _volume_ids(sc))
