@@ -903,6 +903,17 @@ int rt_tga_encode_rgb8(const uint8_t* rgb, uint32_t w, uint32_t h, uint8_t** byt
   int rc = rt::tga_encode_rgb8(rgb, w, h, bytes, len);
   return rc == RT_OK ? RT_OK : fail(rc, "rt_tga_encode_rgb8: bad argument");
 }
+int rt_png_decode(const uint8_t* bytes, size_t len, uint8_t** rgb, uint32_t* w, uint32_t* h) {
+  if (!bytes || !rgb || !w || !h) return fail(RT_ERR_INVALID, "rt_png_decode: bad argument");
+  std::string err;
+  int rc = rt::png_decode(bytes, len, rgb, w, h, err);
+  return rc == RT_OK ? RT_OK : fail(rc, err);
+}
+int rt_png_encode_rgb8(const uint8_t* rgb, uint32_t w, uint32_t h, uint8_t** bytes, size_t* len) {
+  if (!bytes || !len) return fail(RT_ERR_INVALID, "rt_png_encode_rgb8: bad argument");
+  int rc = rt::png_encode_rgb8(rgb, w, h, bytes, len);
+  return rc == RT_OK ? RT_OK : fail(rc, "rt_png_encode_rgb8: bad argument");
+}
 void rt_free(void* p) { std::free(p); }
 
 int rt_mesh_reachability(const float* pos, uint32_t nverts, const uint32_t* idx, uint32_t ntris, uint8_t* mask) {

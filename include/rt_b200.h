@@ -245,6 +245,10 @@ void rt_obj_free(rt_obj_mesh* m);
 /* TGA (types 2,3,10,11; 8/24/32 bpp) -> RGB8 top-down; *rgb is malloc'ed, free with rt_free */
 int rt_tga_decode(const uint8_t* bytes, size_t len, uint8_t** rgb, uint32_t* w, uint32_t* h);
 int rt_tga_encode_rgb8(const uint8_t* rgb, uint32_t w, uint32_t h, uint8_t** bytes, size_t* len);
+/* PNG (non-interlaced; grey / RGB / palette / alpha, 1-16 bit) -> RGB8 top-down, and RGB8 -> PNG (stored deflate).
+ * Self-contained inflate, no zlib.  What image::open (texture.rs:17) and save_with_format (tracing.rs:546) do. */
+int rt_png_decode(const uint8_t* bytes, size_t len, uint8_t** rgb, uint32_t* w, uint32_t* h);
+int rt_png_encode_rgb8(const uint8_t* rgb, uint32_t w, uint32_t h, uint8_t** bytes, size_t* len);
 void rt_free(void* p);
 
 /* Reachability mask of the reference's index-order BVH (geometry.rs:190-217 with the

@@ -120,7 +120,7 @@ struct Isotropic : Material {  // materials.rs:152-157
 };
 using MaterialRef = std::shared_ptr<const Material>;
 
-// ---- texture (texture.rs).  Only TGA is decoded natively (the library's reader); PNG/JPEG callers pass decoded RGB8.
+// ---- texture (texture.rs).  PNG and TGA are decoded natively (the library's readers); JPEG callers pass decoded RGB8.
 struct Texture {
   uint32_t width = 0, height = 0;
   std::vector<uint8_t> rgb8;
@@ -130,7 +130,9 @@ struct Texture {
     std::vector<uint8_t> bytes((std::istreambuf_iterator<char>(f)), std::istreambuf_iterator<char>());
     uint8_t* px = nullptr;
     uint32_t w = 0, h = 0;
-    if (rt_tga_decode(bytes.data(), bytes.size(), &px, &w, &h) != RT_OK) return std::nullopt;
+    bool png = bytes.size() > 8 && bytes[0] == 137 && bytes[1] == 'P' && bytes[2] == 'N' && bytes[3] == 'G';
+    int rc = png ? rt_png_decode(bytes.data(), bytes.size(), &px, &w, &h) : rt_tga_decode(bytes.data(), bytes.size(), &px, &w, &h);
+    if (rc != RT_OK) return std::nullopt;
     Texture t;
     t.width = w; t.height = h;
     t.rgb8.assign(px, px + (size_t)w * h * 3);
@@ -270,6 +272,14 @@ struct Camera {  // tracing.rs:138-155, same field names, HEAD's defaults (traci
 struct RgbImage {  // image::RgbImage: row 0 = top
   uint32_t width = 0, height = 0;
   std::vector<uint8_t> data;
+  void save_png(const std::string& path) const {  // save_with_format("render.png", ImageFormat::Png), tracing.rs:546
+    uint8_t* bytes = nullptr;
+    size_t len = 0;
+    check(rt_png_encode_rgb8(data.data(), width, height, &bytes, &len));
+    std::ofstream f(path, std::ios::binary);
+    f.write((const char*)bytes, (std::streamsize)len);
+    rt_free(bytes);
+  }
   void save_tga(const std::string& path) const {
     uint8_t* bytes = nullptr;
     size_t len = 0;

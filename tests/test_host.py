@@ -127,6 +127,30 @@ def test_tga_roundtrip_and_variants():
     assert rt.Texture.load_from_file("/nonexistent/Drone_Albedo.tga") is None     # texture.rs:22-24: silently None
 
 
+def test_png_reader_and_writer_against_pil(tmp_path):
+    import io
+    from PIL import Image
+    for name in ("green.png", "white.png", "normal_test.png"):          # palette and RGB files of the reference
+        data = open(scenes.tex_path(name), "rb").read()
+        want = np.asarray(Image.open(io.BytesIO(data)).convert("RGB"), dtype=np.uint8)
+        assert np.array_equal(_ffi.png_decode(data), want), name
+    rng = np.random.RandomState(1)
+    img = rng.randint(0, 256, size=(37, 91, 3)).astype(np.uint8)
+    for mode, kw in (("RGB", {}), ("RGBA", {}), ("L", {}), ("P", {}), ("1", {}), ("I;16", {}), ("RGB", dict(compress_level=0))):
+        im = Image.fromarray(img).convert(mode) if mode != "I;16" else Image.fromarray((img[..., 0].astype(np.uint16) * 257))
+        buf = io.BytesIO()
+        im.save(buf, format="PNG", **kw)
+        want = np.asarray(im.convert("RGB") if mode != "I;16" else Image.fromarray(img[..., 0]).convert("RGB"), dtype=np.uint8)
+        assert np.array_equal(_ffi.png_decode(buf.getvalue()), want), mode
+    enc = _ffi.png_encode(img)                                           # our writer, PIL as the reader
+    assert np.array_equal(np.asarray(Image.open(io.BytesIO(enc)).convert("RGB")), img)
+    assert np.array_equal(_ffi.png_decode(enc), img)
+    big = rng.randint(0, 256, size=(300, 301, 3)).astype(np.uint8)       # more than one 64 KiB stored block
+    assert np.array_equal(np.asarray(Image.open(io.BytesIO(_ffi.png_encode(big))).convert("RGB")), big)
+    with pytest.raises(_ffi.RtError):
+        _ffi.png_decode(b"\x89PNG\r\n\x1a\n" + b"\x00" * 40)
+
+
 def test_reference_textures_decode():
     for name, size in (("green.png", (225, 225)), ("magenta.jpg", (615, 615)), ("normal_test.png", (512, 512))):
         t = rt.Texture.load_from_file(scenes.tex_path(name))
