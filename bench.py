@@ -45,6 +45,7 @@ def parse_args():
     ap.add_argument("--spp", type=int, default=0, help="override samples per pixel (invalidates the headline)")
     ap.add_argument("--width", type=int, default=0)
     ap.add_argument("--height", type=int, default=0)
+    ap.add_argument("--depth", type=int, default=0, help="override path_depth (diagnostics; invalidates the headline)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=20.0, help="target CPU time of the cpu_baseline sample")
@@ -60,6 +61,8 @@ def scene_for(args):
         kw["width"] = args.width
     if args.height:
         kw["height"] = args.height
+    if args.depth:
+        kw["depth"] = args.depth
     return scenes.make_scene(args.workload, **kw), scenes.DESCRIPTIONS[args.workload]
 
 

@@ -38,6 +38,22 @@ namespace rt {
 #ifndef RT_STACK_DIST
 #define RT_STACK_DIST 0
 #endif
+// RT_STREAM_HINTS: ray queue / hit record traffic uses the streaming (evict-first) cache operators so that it does
+// not push BVH nodes, triangles and texels out of L1/L2.  RT_PREFETCH_FAR: prefetch the children of the child that
+// is pushed on the stack.
+#ifndef RT_STREAM_HINTS
+#define RT_STREAM_HINTS 1
+#endif
+#ifndef RT_PREFETCH_FAR
+#define RT_PREFETCH_FAR 0
+#endif
+#if RT_STREAM_HINTS
+#define RT_LDS(p) __ldcs(p)
+#define RT_STS(p, v) __stcs(p, v)
+#else
+#define RT_LDS(p) (*(p))
+#define RT_STS(p, v) (*(p) = (v))
+#endif
 #ifndef RT_OCTANT_SORT
 #define RT_OCTANT_SORT 1
 #endif
@@ -367,8 +383,13 @@ __device__ __forceinline__ void trav_interior(const rt_dev_scene& sc, Trav& T) {
   uint32_t el = fbits(l0.w), er = fbits(r0.w);
   if (hl && hr) {
     bool lfirst = tl <= tr;
-    T.push(lfirst ? er : el, lfirst ? tr : tl);
+    uint32_t far = lfirst ? er : el;
+    T.push(far, lfirst ? tr : tl);
     T.entry = lfirst ? el : er;
+#if RT_PREFETCH_FAR
+    if (!(far & RT_LEAF_FLAG))
+      asm volatile("prefetch.global.L1 [%0];" ::"l"(reinterpret_cast<const float4*>(sc.nodes) + (size_t)far * 2u));
+#endif
   } else {
     T.entry = hl ? el : (hr ? er : RT_ENTRY_NONE);
   }
@@ -718,9 +739,10 @@ __global__ void __launch_bounds__(RT_BLOCK) k_raygen(rt_frame fr, rt_ctrl* __res
 
 template <bool COUNT>
 __global__ void __launch_bounds__(RT_BLOCK, RT_EXTEND_MIN_BLOCKS) k_trace(rt_dev_scene sc, rt_frame fr, rt_ctrl* __restrict__ ctrl,
-                                                                        rt_paths cur, rt_hits hits) {
+                                                                        rt_paths cur, rt_hits hits, const uint32_t* __restrict__ order) {
   __shared__ __align__(8) uint32_t sstack[(RT_SMEM_STACK * (RT_STACK_DIST ? 2 : 1) + 6) * RT_BLOCK];
   const uint32_t n_rays = ctrl->n_rays;
+  const uint32_t n_sorted = fr.sort_enabled ? ctrl->n_cont : 0u;  // continuing rays are visited in sorted order
   const uint32_t lane = threadIdx.x & 31u;
   const uint32_t FULL = 0xFFFFFFFFu;
   uint32_t lstack[RT_LOCAL_STACK * (RT_STACK_DIST ? 2 : 1)];
@@ -740,8 +762,8 @@ __global__ void __launch_bounds__(RT_BLOCK, RT_EXTEND_MIN_BLOCKS) k_trace(rt_dev
     // ---- retire finished lanes: the compact hit record is all k_shade needs to redo the rest
     if (have && fin) {
       const Best& best = T.best;
-      hits.H[T.slot] = make_float4(best.t, best.u, best.v, __uint_as_float(best.prim));
-      hits.obj[T.slot] = best.obj;
+      RT_STS(&hits.H[T.slot], make_float4(best.t, best.u, best.v, __uint_as_float(best.prim)));
+      RT_STS(&hits.obj[T.slot], best.obj);
       if (COUNT) {
         atomicAdd(&ctrl->counters[0], (unsigned long long)T.cnt.nodes);
         atomicAdd(&ctrl->counters[1], (unsigned long long)T.cnt.tris);
@@ -772,7 +794,8 @@ __global__ void __launch_bounds__(RT_BLOCK, RT_EXTEND_MIN_BLOCKS) k_trace(rt_dev
       }
       uint32_t my = c_next + __popc(need & ((1u << lane) - 1u));
       if (!have && my < c_end) {
-        float4 a = cur.A[my], b = cur.B[my];
+        if (my < n_sorted) my = __ldg(order + my);  // queue position -> slot
+        float4 a = RT_LDS(&cur.A[my]), b = RT_LDS(&cur.B[my]);
         f3 wo = mk(a.x, a.y, a.z), wd = mk(a.w, b.x, b.y);
         if (wd.x == 0.0f && wd.y == 0.0f && wd.z == 0.0f && b.z == 0.0f) {
           hits.obj[my] = -1;  // "no ray" marker written by k_raygen
@@ -907,6 +930,20 @@ __device__ __forceinline__ f3 sample_hemisphere(f3 n, f3 ball) {
   return cross(v, tmp) * 2.0f + dir;
 }
 
+// Sort key of a scattered ray: a 15-bit spatial hash of the cell its origin lies in (cells of 1/16 of the TLAS
+// box, NOT clamped to the box - floors and walls extend far beyond it and clamping would pile their rays into a few
+// boundary bins) and the octant of its direction.  Rays that start close together and head the same way fetch the
+// same nodes, so a k_trace warp built from one bin stays together much longer than 32 rays in material-queue order.
+__device__ __forceinline__ uint32_t ray_sort_key(const rt_frame& fr, f3 o, f3 d) {
+  int cx = __float2int_rd((o.x - fr.sort_min[0]) * fr.sort_scale[0]);
+  int cy = __float2int_rd((o.y - fr.sort_min[1]) * fr.sort_scale[1]);
+  int cz = __float2int_rd((o.z - fr.sort_min[2]) * fr.sort_scale[2]);
+  uint32_t h = ((uint32_t)cx * 73856093u) ^ ((uint32_t)cy * 19349663u) ^ ((uint32_t)cz * 83492791u);
+  h = (h ^ (h >> 15)) & 0x7FFFu;
+  uint32_t oct = fr.sort_use_octant ? ((d.x < 0.0f ? 1u : 0u) | (d.y < 0.0f ? 2u : 0u) | (d.z < 0.0f ? 4u : 0u)) : 0u;
+  return (h << 3) | oct;
+}
+
 // fixed-point accumulation (2^-30 units): order-independent, hence reproducible and shardable
 #define RT_FIX_SCALE 1073741824.0f
 #define RT_FIX_CLAMP 65536.0f
@@ -934,7 +971,8 @@ __device__ __forceinline__ void accum_add(long long* accum, uint32_t pixel, f3 c
 template <bool COUNT>
 __global__ void __launch_bounds__(RT_BLOCK, RT_SHADE_MIN_BLOCKS) k_shade(rt_dev_scene sc, rt_frame fr, rt_ctrl* __restrict__ ctrl,
                                                     rt_paths cur, rt_paths nxt, rt_hits hits,
-                                                    const uint32_t* __restrict__ queues, long long* __restrict__ accum) {
+                                                    const uint32_t* __restrict__ queues, long long* __restrict__ accum,
+                                                    rt_sortbuf sort) {
 #if RT_OCTANT_SORT
   __shared__ uint32_t s_ocount[8][RT_WARPS];
 #else
@@ -973,8 +1011,8 @@ __global__ void __launch_bounds__(RT_BLOCK, RT_SHADE_MIN_BLOCKS) k_shade(rt_dev_
   f3 no, nd, nT;
   uint32_t pixel = 0, sb = 0;
   if (j < count) {
-    uint32_t slot = queues[(size_t)cls * fr.capacity + j];
-    float4 a = cur.A[slot], bq = cur.B[slot], c = cur.C[slot];
+    uint32_t slot = RT_LDS(&queues[(size_t)cls * fr.capacity + j]);
+    float4 a = RT_LDS(&cur.A[slot]), bq = RT_LDS(&cur.B[slot]), c = RT_LDS(&cur.C[slot]);
     f3 o = mk(a.x, a.y, a.z);
     f3 d = mk(a.w, bq.x, bq.y);
     f3 T = mk(bq.z, bq.w, c.x);
@@ -982,10 +1020,10 @@ __global__ void __launch_bounds__(RT_BLOCK, RT_SHADE_MIN_BLOCKS) k_shade(rt_dev_
     sb = fbits(c.z);
     uint32_t sample = sb & 0xFFFFFFu, bounce = sb >> 24;
     // hit resolution: what the reference attaches to its RayHit
-    float4 hr = hits.H[slot];
+    float4 hr = RT_LDS(&hits.H[slot]);
     Best best;
     best.t = hr.x; best.u = hr.y; best.v = hr.z; best.prim = fbits(hr.w);
-    best.obj = hits.obj[slot];
+    best.obj = RT_LDS(&hits.obj[slot]);
     Surface sf;
     resolve_hit<COUNT>(sc, o, d, best, sf, ctrl->counters);
     f3 hp = sf.hp, n = sf.n;
@@ -1122,10 +1160,89 @@ __global__ void __launch_bounds__(RT_BLOCK, RT_SHADE_MIN_BLOCKS) k_shade(rt_dev_
   if (alive) {
     uint32_t pos = s_base + s_wcount[warp] + __popc(bal & ((1u << lane) - 1u));
 #endif
-    nxt.A[pos] = make_float4(no.x, no.y, no.z, nd.x);
-    nxt.B[pos] = make_float4(nd.y, nd.z, nT.x, nT.y);
-    nxt.C[pos] = make_float4(nT.z, __uint_as_float(pixel), __uint_as_float(sb), 0.0f);
+    RT_STS(&nxt.A[pos], make_float4(no.x, no.y, no.z, nd.x));
+    RT_STS(&nxt.B[pos], make_float4(nd.y, nd.z, nT.x, nT.y));
+    RT_STS(&nxt.C[pos], make_float4(nT.z, __uint_as_float(pixel), __uint_as_float(sb), 0.0f));
+    if (fr.sort_enabled) {
+      // one atomic per distinct key per warp: the rays of a warp mostly leave the same few cells
+      uint32_t key = ray_sort_key(fr, no, nd);
+      sort.keys[pos] = key;
+      uint32_t peers = __match_any_sync(__activemask(), key);
+      if ((peers & ((1u << lane) - 1u)) == 0) atomicAdd(&sort.hist[key], (uint32_t)__popc(peers));
+    }
   }
+}
+
+// ------------------------------------------------------------------ k_raysort_scan / k_raysort_scatter
+// counting sort of the next ray queue by ray_sort_key: k_shade has filled the histogram.  k_raysort_scan: one block
+// per 1024 bins turns its slice into exclusive offsets within the slice (coalesced), clears the histogram for the next
+// iteration and records the slice total.  k_raysort_scatter: every block first prefixes the slice totals (at most
+// RT_SORT_BINS/1024 of them), then every ray claims a place in its bin - one atomic per distinct key per warp.
+__global__ void __launch_bounds__(1024) k_raysort_scan(rt_sortbuf sort) {
+  __shared__ uint32_t s_warp[32];
+  const uint32_t bin = blockIdx.x * 1024u + threadIdx.x;
+  const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+  uint32_t v = sort.hist[bin];
+  sort.hist[bin] = 0;
+  uint32_t inc = v;  // inclusive scan inside the warp
+#pragma unroll
+  for (int off = 1; off < 32; off <<= 1) {
+    uint32_t t = __shfl_up_sync(0xFFFFFFFFu, inc, off);
+    if (lane >= (uint32_t)off) inc += t;
+  }
+  if (lane == 31) s_warp[warp] = inc;
+  __syncthreads();
+  if (warp == 0) {
+    uint32_t w = s_warp[lane], winc = w;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+      uint32_t t = __shfl_up_sync(0xFFFFFFFFu, winc, off);
+      if (lane >= (uint32_t)off) winc += t;
+    }
+    s_warp[lane] = winc - w;  // exclusive prefix of the warps
+    if (lane == 31) sort.slice_total[blockIdx.x] = winc;
+  }
+  __syncthreads();
+  sort.cursor[bin] = s_warp[warp] + inc - v;  // exclusive offset inside this slice
+}
+__global__ void __launch_bounds__(256) k_raysort_scatter(rt_ctrl* __restrict__ ctrl, rt_sortbuf sort) {
+  __shared__ uint32_t s_slice[RT_SORT_BINS / 1024u];
+  const uint32_t i = blockIdx.x * 256u + threadIdx.x;
+  if (blockIdx.x * 256u >= ctrl->n_next) return;
+  const uint32_t lane = threadIdx.x & 31u;
+  if (threadIdx.x < 32) {  // exclusive prefix of the slice totals (RT_SORT_BINS / 1024 <= 32 * per-lane count)
+    const uint32_t per = (RT_SORT_BINS / 1024u + 31u) / 32u;
+    uint32_t sum = 0, loc[per];
+#pragma unroll
+    for (uint32_t k = 0; k < per; ++k) {
+      uint32_t idx = lane * per + k;
+      loc[k] = idx < RT_SORT_BINS / 1024u ? sort.slice_total[idx] : 0u;
+      sum += loc[k];
+    }
+    uint32_t inc = sum;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+      uint32_t t = __shfl_up_sync(0xFFFFFFFFu, inc, off);
+      if (lane >= (uint32_t)off) inc += t;
+    }
+    uint32_t base = inc - sum;
+#pragma unroll
+    for (uint32_t k = 0; k < per; ++k) {
+      uint32_t idx = lane * per + k;
+      if (idx < RT_SORT_BINS / 1024u) s_slice[idx] = base;
+      base += loc[k];
+    }
+  }
+  __syncthreads();
+  if (i >= ctrl->n_next) return;
+  // neighbouring queue positions come from the same k_shade block and share keys: one atomic per distinct key per warp
+  uint32_t key = sort.keys[i];
+  uint32_t peers = __match_any_sync(__activemask(), key);
+  uint32_t leader = __ffs(peers) - 1u;
+  uint32_t base = 0;
+  if (lane == leader) base = atomicAdd(&sort.cursor[key], (uint32_t)__popc(peers));
+  base = __shfl_sync(peers, base, leader);
+  sort.order[s_slice[key >> 10] + base + __popc(peers & ((1u << lane) - 1u))] = i;
 }
 
 // ------------------------------------------------------------------ k_resolve (Q12)
@@ -1197,12 +1314,17 @@ int trace_blocks_per_sm() {
 void launch_raygen(const rt_frame& fr, rt_ctrl* ctrl, rt_paths cur, cudaStream_t st) {
   k_raygen<<<(fr.capacity + RT_BLOCK - 1) / RT_BLOCK, RT_BLOCK, 0, st>>>(fr, ctrl, cur);
 }
-void launch_trace(const rt_dev_scene& sc, const rt_frame& fr, rt_ctrl* ctrl, rt_paths cur, rt_hits hits, bool count,
-                  uint32_t persistent_blocks, cudaStream_t st) {
+void launch_trace(const rt_dev_scene& sc, const rt_frame& fr, rt_ctrl* ctrl, rt_paths cur, rt_hits hits, rt_sortbuf sort,
+                  bool count, uint32_t persistent_blocks, cudaStream_t st) {
   uint32_t full = (fr.capacity + RT_BLOCK - 1) / RT_BLOCK;
   uint32_t grid = full < persistent_blocks ? full : persistent_blocks;  // never more blocks than there could be rays
-  if (count) k_trace<true><<<grid, RT_BLOCK, 0, st>>>(sc, fr, ctrl, cur, hits);
-  else k_trace<false><<<grid, RT_BLOCK, 0, st>>>(sc, fr, ctrl, cur, hits);
+  if (count) k_trace<true><<<grid, RT_BLOCK, 0, st>>>(sc, fr, ctrl, cur, hits, sort.order);
+  else k_trace<false><<<grid, RT_BLOCK, 0, st>>>(sc, fr, ctrl, cur, hits, sort.order);
+}
+void launch_raysort(const rt_frame& fr, rt_ctrl* ctrl, rt_sortbuf sort, cudaStream_t st) {
+  if (!fr.sort_enabled) return;
+  k_raysort_scan<<<RT_SORT_BINS / 1024u, 1024, 0, st>>>(sort);
+  k_raysort_scatter<<<(fr.capacity + 255) / 256, 256, 0, st>>>(ctrl, sort);
 }
 void launch_sort(const rt_dev_scene& sc, const rt_frame& fr, rt_ctrl* ctrl, rt_hits hits, uint32_t* queues, cudaStream_t st) {
   k_sort<<<(fr.capacity + RT_SORT_BLOCK - 1) / RT_SORT_BLOCK, RT_SORT_BLOCK, 0, st>>>(sc, fr, ctrl, hits.obj, queues);
@@ -1212,10 +1334,10 @@ void launch_surface(const rt_dev_scene& sc, const rt_frame& fr, rt_ctrl* ctrl, r
   k_surface<<<(fr.capacity + RT_BLOCK - 1) / RT_BLOCK, RT_BLOCK, 0, st>>>(sc, ctrl, cur, hits, dbg);
 }
 void launch_shade(const rt_dev_scene& sc, const rt_frame& fr, rt_ctrl* ctrl, rt_paths cur, rt_paths nxt, rt_hits hits,
-                  const uint32_t* queues, long long* accum, bool count, cudaStream_t st) {
+                  const uint32_t* queues, long long* accum, rt_sortbuf sort, bool count, cudaStream_t st) {
   uint32_t grid = (fr.capacity + RT_BLOCK - 1) / RT_BLOCK + RT_NUM_CLASSES;
-  if (count) k_shade<true><<<grid, RT_BLOCK, 0, st>>>(sc, fr, ctrl, cur, nxt, hits, queues, accum);
-  else k_shade<false><<<grid, RT_BLOCK, 0, st>>>(sc, fr, ctrl, cur, nxt, hits, queues, accum);
+  if (count) k_shade<true><<<grid, RT_BLOCK, 0, st>>>(sc, fr, ctrl, cur, nxt, hits, queues, accum, sort);
+  else k_shade<false><<<grid, RT_BLOCK, 0, st>>>(sc, fr, ctrl, cur, nxt, hits, queues, accum, sort);
 }
 void launch_resolve(const long long* accum, uint32_t npix, uint32_t spp, float gamma, float* out_linear,
                     uint8_t* out_rgb8, cudaStream_t st) {

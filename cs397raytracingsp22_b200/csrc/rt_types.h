@@ -30,6 +30,7 @@
 #define RT_LEAF_FLAG 0x80000000u
 #define RT_ENTRY_NONE 0xFFFFFFFFu
 #define RT_ENTRY_RESTORE 0xFFFFFFFEu
+#define RT_SORT_BINS 262144u  /* 15-bit spatial hash of the origin cell << 3 | direction octant */
 #define RT_MAX_LEAF_TRIS 8  /* fits the 4-bit count of a packed stack entry */
 
 enum rt_obj_kind { RT_OBJ_MESH = 0, RT_OBJ_SPHERE = 1, RT_OBJ_TRIANGLE = 2, RT_OBJ_PLANE = 3, RT_OBJ_VOLUME = 4 };
@@ -98,6 +99,11 @@ struct rt_frame {
   uint32_t shard_mode, shard_rank, shard_count, tile_size, tiles_x, tiles_y;
   uint32_t sample_begin, sample_count;
   uint32_t capacity;                // wavefront width P
+  // secondary-ray sorting (k_shade -> k_raysort_*): origin cell (16^3 over the TLAS box, Morton order) | direction octant
+  uint32_t sort_enabled;
+  float sort_min[3], sort_scale[3];
+  float sort_cells_m1;              // cells per axis - 1 (<= 15)
+  uint32_t sort_use_octant;
 };
 
 #endif

@@ -15,7 +15,7 @@ for lib in libs:
             a, b = kv.split("=")
             env[a] = b
         r = subprocess.run([sys.executable, "bench.py", "--steps", "2", "--warmup", "2", "--spp", "256", "--no-cpu-baseline", "--no-e2e"]
-                           + (["--workload", env["WORKLOAD"]] if "WORKLOAD" in env else []) + ["--wavefront", env.get("WAVEFRONT", "8388608")],
+                           + (["--workload", env["WORKLOAD"]] if "WORKLOAD" in env else []) + ["--wavefront", env.get("WAVEFRONT", "8388608")] + (["--depth", env["DEPTH"]] if "DEPTH" in env else []),
                            env=env, capture_output=True, text=True)
         try:
             d = json.loads(r.stdout.strip().splitlines()[-1])
