@@ -714,8 +714,8 @@ int rt_render_accum(rt_scene* s, const rt_camera* cam, const rt_render_opts* opt
     int cells = 32;
     if (const char* e = std::getenv("RT_SORT_CELLS")) cells = std::max(1, std::min(1024, std::atoi(e)));
     fr.sort_cells_m1 = (float)(cells - 1);
-    fr.sort_use_octant = 1;
-    if (const char* e = std::getenv("RT_SORT_OCTANT")) fr.sort_use_octant = std::atoi(e) ? 1u : 0u;
+    fr.sort_use_octant = 2;  // 0: cell only, 1: + octant, 2: + octant and dominant axis (measured best)
+    if (const char* e = std::getenv("RT_SORT_OCTANT")) fr.sort_use_octant = (uint32_t)std::max(0, std::min(2, std::atoi(e)));
     float grow = 0.0f;  // RT_SORT_GROW: enlarge the cell grid beyond the TLAS box by this fraction of its extent per side
     if (const char* e = std::getenv("RT_SORT_GROW")) grow = (float)std::atof(e);
     for (int k = 0; k < 3; ++k) {

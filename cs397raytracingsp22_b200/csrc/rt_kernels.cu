@@ -939,9 +939,16 @@ __device__ __forceinline__ uint32_t ray_sort_key(const rt_frame& fr, f3 o, f3 d)
   int cy = __float2int_rd((o.y - fr.sort_min[1]) * fr.sort_scale[1]);
   int cz = __float2int_rd((o.z - fr.sort_min[2]) * fr.sort_scale[2]);
   uint32_t h = ((uint32_t)cx * 73856093u) ^ ((uint32_t)cy * 19349663u) ^ ((uint32_t)cz * 83492791u);
+  uint32_t oct = (d.x < 0.0f ? 1u : 0u) | (d.y < 0.0f ? 2u : 0u) | (d.z < 0.0f ? 4u : 0u);
+  if (fr.sort_use_octant == 2u) {
+    // 5 direction bits: octant + dominant axis (24 classes = the 6 cube faces x 4 quadrants), 13-bit cell hash
+    float ax = fabsf(d.x), ay = fabsf(d.y), az = fabsf(d.z);
+    uint32_t dom = (ax >= ay && ax >= az) ? 0u : (ay >= az ? 1u : 2u);
+    h = (h ^ (h >> 13)) & 0x1FFFu;
+    return (h << 5) | (dom << 3) | oct;
+  }
   h = (h ^ (h >> 15)) & 0x7FFFu;
-  uint32_t oct = fr.sort_use_octant ? ((d.x < 0.0f ? 1u : 0u) | (d.y < 0.0f ? 2u : 0u) | (d.z < 0.0f ? 4u : 0u)) : 0u;
-  return (h << 3) | oct;
+  return (h << 3) | (fr.sort_use_octant ? oct : 0u);
 }
 
 // fixed-point accumulation (2^-30 units): order-independent, hence reproducible and shardable
