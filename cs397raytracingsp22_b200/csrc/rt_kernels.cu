@@ -154,8 +154,15 @@ __device__ __forceinline__ void camera_ray(const rt_frame& fr, uint32_t x, uint3
 // work index -> (pixel, sample); false when a tile slot falls outside the image
 __device__ __forceinline__ bool work_to_pixel(const rt_frame& fr, unsigned long long g, uint32_t& x, uint32_t& y,
                                               uint32_t& sample) {
-  unsigned long long pl = g / fr.sample_count;
-  sample = fr.sample_begin + (uint32_t)(g - pl * fr.sample_count);
+  unsigned long long pl;
+  if (g < 0x100000000ull) {  // 32-bit division is several times cheaper and covers shards of up to 4 Gi paths
+    uint32_t q = (uint32_t)g / fr.sample_count;
+    pl = q;
+    sample = fr.sample_begin + ((uint32_t)g - q * fr.sample_count);
+  } else {
+    pl = g / fr.sample_count;
+    sample = fr.sample_begin + (uint32_t)(g - pl * fr.sample_count);
+  }
   if (fr.shard_mode == RT_SHARD_TILES) {
     uint32_t ts = fr.tile_size, ts2 = ts * ts;
     uint32_t k = (uint32_t)(pl / ts2), within = (uint32_t)(pl - (unsigned long long)k * ts2);
