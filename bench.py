@@ -301,9 +301,16 @@ def main():
         rgb_h = torch.empty((H, W, 3), dtype=torch.uint8).pin_memory()
         scene_bytes = g.device_bytes()
 
+        lin_np, rgb_np = lin_h.numpy(), rgb_h.numpy()
+
         def e2e_step():
-            g.upload()                                   # host -> device: the lowered scene
-            out = step(opts_for())
+            g.upload()                                   # host -> device: the lowered scene (rt_scene_upload)
+            if world == 1:
+                # the public host-buffer call, exactly what Scene::render_to_image's replacement makes: rt_render
+                # renders, resolves and copies the linear and RGB8 images into the caller's (pinned) host buffers
+                g.render(cam, opts_for(), out_linear=lin_np, out_rgb8=rgb_np)
+                return
+            out = step(opts_for())                       # N>1: rt_render_accum per rank + NCCL reduce + rt_resolve
             if rank == 0:
                 lin_h.copy_(out[0], non_blocking=True)   # device -> host: linear radiance + RGB8 image
                 rgb_h.copy_(out[1], non_blocking=True)
@@ -323,7 +330,9 @@ def main():
             dt = float(t.item())
         e2e = {"value": (job_samples / args.steps) * n_e2e / dt / 1e6, "unit": UNIT,
                "h2d_bytes_per_step": int(scene_bytes + 512), "d2h_bytes_per_step": int(W * H * 3 * 5),
-               "steps": n_e2e, "call": "rt_scene_upload + rt_render_accum + rt_resolve + copy to pinned host buffers"}
+               "steps": n_e2e,
+               "call": ("rt_scene_upload + rt_render (host buffers in, host images out)" if world == 1 else
+                        "rt_scene_upload + rt_render_accum per rank + NCCL reduce + rt_resolve + copy to pinned host buffers")}
 
     if rank != 0:
         if world > 1:

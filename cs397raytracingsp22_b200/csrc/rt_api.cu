@@ -538,6 +538,9 @@ int rt_add_instance(rt_scene* s, int mesh, const float xform[16], const float* i
   if (!s || !xform) return fail(RT_ERR_INVALID, "rt_add_instance: bad argument");
   if (mesh < 0 || mesh >= (int)s->meshes.size()) return fail(RT_ERR_INVALID, "rt_add_instance: bad mesh id");
   if (material >= (int)s->materials.size()) return fail(RT_ERR_INVALID, "rt_add_instance: bad material id");
+  if (xform[3] != 0.0f || xform[7] != 0.0f || xform[11] != 0.0f || xform[15] != 1.0f ||
+      (inv_xform && (inv_xform[3] != 0.0f || inv_xform[7] != 0.0f || inv_xform[11] != 0.0f || inv_xform[15] != 1.0f)))
+    return fail(RT_ERR_UNSUPPORTED, "rt_add_instance: only affine transforms (last row 0 0 0 1) are supported");
   rt::HostObject o;
   o.kind = RT_OBJ_MESH;
   o.mesh = mesh;

@@ -55,6 +55,12 @@ def test_bad_arguments_return_codes_not_crashes(rtlib):
         b.add_instance(3, np.eye(4, dtype=np.float32).reshape(-1), np.eye(4, dtype=np.float32).reshape(-1), m, [-1] * 5)
     with pytest.raises(_ffi.RtError):
         b.add_mesh(np.zeros((3, 3)), np.zeros((3, 3)), np.zeros((3, 2)), np.array([[0, 1, 7]]))   # index out of range
+    proj = np.eye(4, dtype=np.float32)
+    proj[3, 2] = 0.5                                       # projective transform: refused, not approximated
+    mesh = b.add_mesh(np.eye(3), np.eye(3), np.zeros((3, 2)), np.array([[0, 1, 2]]))
+    with pytest.raises(_ffi.RtError) as e:
+        b.add_instance(mesh, cg.colmajor(proj), cg.colmajor(np.eye(4)), m, [-1] * 5)
+    assert e.value.code == _ffi.RT_ERR_UNSUPPORTED
     assert rtlib.rt_scene_create(None) == _ffi.RT_ERR_INVALID
     assert b"out is NULL" in rtlib.rt_last_error()
 
