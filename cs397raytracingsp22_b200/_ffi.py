@@ -94,6 +94,7 @@ SIGNATURES = {
     "rt_add_triangle": (C.c_int, [_P, _F, _F, _F, C.c_int]),
     "rt_add_plane": (C.c_int, [_P, _F, _F, C.c_int]),
     "rt_add_volume_sphere": (C.c_int, [_P, _F, C.c_float, C.c_float, C.c_int]),
+    "rt_add_volume_mesh": (C.c_int, [_P, C.c_int, _F, _F, C.c_float, C.c_int]),
     "rt_scene_lower": (C.c_int, [_P, C.POINTER(rt_lower_info)]),
     "rt_commit": (C.c_int, [_P, C.c_int]),
     "rt_scene_device_bytes": (C.c_uint64, [_P]),
@@ -297,6 +298,11 @@ class GpuBackend:
     def add_volume_sphere(self, center, radius, density, material) -> int:
         return check(self.lib.rt_add_volume_sphere(self.handle, fptr(f3(center)), float(radius), float(density),
                                                    material))
+
+    def add_volume_mesh(self, mesh, xform_colmajor, inv_colmajor, density, material) -> int:
+        x = np.ascontiguousarray(xform_colmajor, dtype=np.float32).reshape(16)
+        inv = np.ascontiguousarray(inv_colmajor, dtype=np.float32).reshape(16)
+        return check(self.lib.rt_add_volume_mesh(self.handle, mesh, fptr(x), fptr(inv), float(density), material))
 
     def lower_info(self) -> dict:
         """Host-only lowering (no GPU needed): sizes and depths of what rt_commit would upload."""

@@ -606,6 +606,26 @@ int rt_add_volume_sphere(rt_scene* s, const float c[3], float radius, float dens
   return rc;
 }
 
+int rt_add_volume_mesh(rt_scene* s, int mesh, const float xform[16], const float* inv_xform, float density,
+                       int phase_material) {
+  if (!s || !xform) return fail(RT_ERR_INVALID, "rt_add_volume_mesh: bad argument");
+  if (mesh < 0 || mesh >= (int)s->meshes.size()) return fail(RT_ERR_INVALID, "rt_add_volume_mesh: bad mesh id");
+  if (xform[3] != 0.0f || xform[7] != 0.0f || xform[11] != 0.0f || xform[15] != 1.0f ||
+      (inv_xform && (inv_xform[3] != 0.0f || inv_xform[7] != 0.0f || inv_xform[11] != 0.0f || inv_xform[15] != 1.0f)))
+    return fail(RT_ERR_UNSUPPORTED, "rt_add_volume_mesh: only affine transforms (last row 0 0 0 1) are supported");
+  rt::HostObject o;
+  o.kind = RT_OBJ_VOLUME_MESH;
+  o.mesh = mesh;
+  std::memcpy(o.xform, xform, 64);
+  if (inv_xform) std::memcpy(o.inv_xform, inv_xform, 64);
+  else if (!rt::invert_affine_cofactor(xform, o.inv_xform)) return fail(RT_ERR_INVALID, "rt_add_volume_mesh: transform is singular");
+  o.density = density;
+  o.vol_index = s->n_volumes;
+  int rc = add_simple(s, o, phase_material, "rt_add_volume_mesh");
+  if (rc >= 0) s->n_volumes++;
+  return rc;
+}
+
 int rt_scene_upload(rt_scene* s) {
   if (!s || !s->lowered) return fail(RT_ERR_NOT_COMMITTED, "rt_scene_upload: scene has not been lowered (call rt_commit)");
   CUDA_TRY(cudaSetDevice(s->device));
@@ -630,6 +650,8 @@ int rt_scene_upload(rt_scene* s) {
   d.n_planes = (L.planes.size() == 1 && L.planes[0] < 0) ? 0u : (uint32_t)L.planes.size();
   d.n_objects = (uint32_t)s->objects.size();
   d.n_volumes = L.n_volumes;
+  d.n_volume_meshes = 0;
+  for (const auto& o : s->objects) d.n_volume_meshes += o.kind == RT_OBJ_VOLUME_MESH ? 1u : 0u;
   for (int k = 0; k < 3; ++k) {
     d.tlas_min[k] = L.tlas_min[k];
     d.tlas_max[k] = L.tlas_max[k];

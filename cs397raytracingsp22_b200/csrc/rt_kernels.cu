@@ -256,6 +256,8 @@ struct Trav {
   bool in_blas;
   uint32_t sbase;    // shared-space byte address of this thread's stack column ([depth][thread] layout)
   uint32_t wbase;    // shared-space byte address of this thread's saved world-space (inv, oi), 6 words [k][thread]
+  uint32_t vol_phase;  // mesh-bounded volume: 0 = none, 1 = entry query running, 2 = exit query running
+  bool volret;         // pop_next just popped the end-of-query marker
   uint32_t* lstack;  // RT_LOCAL_STACK entries of local memory, declared by the kernel
   Best best;
   Cnt cnt;
@@ -323,12 +325,35 @@ struct Trav {
     inv = mk(v[0], v[1], v[2]);
     oi = mk(v[3], v[4], v[5]);
   }
+  // mesh-bounded volume: the closest hit found so far and t_entr wait in shared memory while the boundary queries run
+  __device__ __forceinline__ void vol_save(const Best& b, float t_entr) const {
+    const uint32_t v[6] = {__float_as_uint(b.t), __float_as_uint(b.u), __float_as_uint(b.v), (uint32_t)b.obj, b.prim,
+                           __float_as_uint(t_entr)};
+#pragma unroll
+    for (int k = 0; k < 6; ++k)
+      asm volatile("st.shared.u32 [%0], %1;" ::"r"(wbase + (6 + k) * (RT_BLOCK * 4u)), "r"(v[k]) : "memory");
+  }
+  __device__ __forceinline__ void vol_load(Best& b, float& t_entr) const {
+    uint32_t v[6];
+#pragma unroll
+    for (int k = 0; k < 6; ++k)
+      asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v[k]) : "r"(wbase + (6 + k) * (RT_BLOCK * 4u)) : "memory");
+    b.t = __uint_as_float(v[0]); b.u = __uint_as_float(v[1]); b.v = __uint_as_float(v[2]);
+    b.obj = (int)v[3]; b.prim = v[4];
+    t_entr = __uint_as_float(v[5]);
+  }
   // pop the next entry; false when the stack is empty.  A RESTORE marker switches back to the
   // world-space ray and leaves entry = NONE (the caller pops again).
+  template <bool VOLMESH>
   __device__ __forceinline__ bool pop_next() {
     if (sp == 0) return false;
     float tn;
     entry = pop(tn);
+    if (VOLMESH && entry == RT_ENTRY_VOLRET) {
+      volret = true;
+      entry = RT_ENTRY_NONE;
+      return true;
+    }
     if (entry == RT_ENTRY_RESTORE) {
       world_ray(o, d);
       load_world_inv();
@@ -403,7 +428,7 @@ __device__ __forceinline__ void trav_interior(const rt_dev_scene& sc, Trav& T) {
 }
 
 // leaf: BLAS leaf = up to RT_MAX_LEAF_TRIS triangle records; TLAS leaf = one top-level object
-template <bool COUNT>
+template <bool COUNT, bool VOLMESH>
 __device__ __forceinline__ void trav_leaf(const rt_dev_scene& sc, Trav& T) {
   const uint32_t first = (T.entry & ~RT_LEAF_FLAG) >> 4, n = T.entry & 15u;
   const float t_min = T.t_min, t_max = T.t_max;
@@ -459,6 +484,34 @@ __device__ __forceinline__ void trav_leaf(const rt_dev_scene& sc, Trav& T) {
         T.set_space(no, nd);
         T.in_blas = true;
         T.cur_obj = obj;
+        T.entry = root;
+      }
+      return;
+    }
+    if (VOLMESH && kind == RT_OBJ_VOLUME_MESH) {
+      // ConvexVolume with a StaticMesh boundary (geometry.rs:505-510): the entry distance is the boundary's closest
+      // hit over ALL t (f32::MIN..f32::MAX), found by traversing its BLAS with that range; k_trace's stack is a
+      // stack, so the query simply nests: park the closest hit so far, run the query, continue in volume_continue()
+      float4 r0 = ldq(sc.objects, q + 1), r1 = ldq(sc.objects, q + 2), r2 = ldq(sc.objects, q + 3);
+      float4 m7 = ldq(sc.objects, q + 7);
+      if (COUNT) T.cnt.inst += 1;
+      f3 no = mk(r0.x * wo.x + r0.y * wo.y + r0.z * wo.z + r0.w * 1.0f, r1.x * wo.x + r1.y * wo.y + r1.z * wo.z + r1.w * 1.0f,
+                 r2.x * wo.x + r2.y * wo.y + r2.z * wo.z + r2.w * 1.0f);
+      f3 nd = mk(r0.x * wd.x + r0.y * wd.y + r0.z * wd.z + r0.w * 0.0f, r1.x * wd.x + r1.y * wd.y + r1.z * wd.z + r1.w * 0.0f,
+                 r2.x * wd.x + r2.y * wd.y + r2.z * wd.z + r2.w * 0.0f);
+      uint32_t root = fbits(m7.x);
+      if (root != RT_ENTRY_NONE) {
+        T.vol_save(T.best, 0.0f);
+        T.push(RT_ENTRY_VOLRET);
+        T.save_world_inv();
+        T.set_space(no, nd);
+        T.in_blas = true;
+        T.cur_obj = obj;
+        T.vol_phase = 1;
+        T.t_min = -CUDART_MAX_NORMAL_F;
+        T.t_max = CUDART_MAX_NORMAL_F;
+        T.best.t = CUDART_MAX_NORMAL_F;
+        T.best.obj = -1;
         T.entry = root;
       }
       return;
@@ -563,6 +616,8 @@ __device__ __forceinline__ void trav_begin(const rt_dev_scene& sc, Trav& T, f3 w
   T.sp = 0;
   T.in_blas = false;
   T.cur_obj = -1;
+  T.vol_phase = 0;
+  T.volret = false;
   // unbounded objects first: a plane hit (the floor is the most common hit of all) shortens the
   // interval before any node is fetched.  Candidate ordering is order independent (see better()).
   test_unbounded<COUNT>(sc, T, wo, wd);
@@ -578,12 +633,75 @@ __device__ __forceinline__ void trav_begin(const rt_dev_scene& sc, Trav& T, f3 w
 // Returns true when the stack is exhausted.  (Measured on B200: postponing leaves until every lane
 // of the warp holds one - "while-while" - is 30 % slower here, because leaves are cheap (1.9
 // triangle tests per ray) compared with the descent they would make the other lanes wait for.)
+// A boundary query of a mesh-bounded volume has finished (its end marker was popped).  Phase 1 found t_entr: start
+// the exit query from t_entr + 1e-4 (geometry.rs:508).  Phase 2 found t_exit: the rest of ConvexVolume::intersect_ray
+// (geometry.rs:512-525) with the ray's own t-range, then back to the world-space traversal.
 template <bool COUNT>
-__device__ __forceinline__ bool trav_round(const rt_dev_scene& sc, Trav& T) {
+__device__ __forceinline__ void volume_continue(const rt_dev_scene& sc, Trav& T, float ray_t_min, float ray_t_max) {
+  T.volret = false;
+  const int obj = T.cur_obj;
+  const uint32_t q = (uint32_t)obj * RT_OBJ_QUADS;
+  Best saved;
+  float t_entr;
+  T.vol_load(saved, t_entr);
+  if (T.vol_phase == 1 && T.best.obj >= 0) {
+    t_entr = T.best.t;
+    T.vol_save(saved, t_entr);  // the parked closest hit stays parked; t_entr joins it
+    uint32_t root = fbits(ldq(sc.objects, q + 7).x);
+    T.push(RT_ENTRY_VOLRET);
+    T.vol_phase = 2;
+    T.t_min = t_entr + 0.0001f;
+    T.t_max = CUDART_MAX_NORMAL_F;
+    T.best.t = CUDART_MAX_NORMAL_F;
+    T.best.obj = -1;
+    T.entry = root;
+    return;
+  }
+  // either no entry hit, or the exit query is done
+  bool have_exit = T.vol_phase == 2 && T.best.obj >= 0;
+  float t_exit = T.best.t;
+  T.best = saved;
+  T.t_min = ray_t_min;
+  T.t_max = ray_t_max;
+  T.vol_phase = 0;
+  T.world_ray(T.o, T.d);
+  T.load_world_inv();
+  T.in_blas = false;
+  T.entry = RT_ENTRY_NONE;
+  if (have_exit && !(t_exit < ray_t_min || t_entr > ray_t_max)) {
+    float4 q9 = ldq(sc.objects, q + 9);
+    float t_start = fmaxf(t_entr, ray_t_min);
+    float t_end = fminf(t_exit, ray_t_max);
+    float dist_in = t_end - t_start;
+    uint32_t vi = fbits(q9.y);
+    float4 kc = T.qC[T.slot];
+    uint32_t pixel = fbits(kc.y), sb = fbits(kc.z);
+    u4 rr = philox4x32_10(pixel, sb & 0xFFFFFFu, sb >> 24, 1u + (vi >> 2), T.k0, T.k1);
+    uint32_t w = (vi & 3u) == 0 ? rr.x : ((vi & 3u) == 1 ? rr.y : ((vi & 3u) == 2 ? rr.z : rr.w));
+    float dist_before = (-1.0f / q9.x) * logf(u01(w));
+    if (dist_before < dist_in) {
+      float t = t_start + dist_before;
+      if (better(t, obj, 0u, T.best)) {
+        T.best.t = t; T.best.obj = obj; T.best.prim = 0;
+      }
+    }
+  }
+}
+
+// one round: descend while interior, then the leaf this lane reached (if any), then pop.
+// Returns true when the stack is exhausted.  (Measured on B200: postponing leaves until every lane
+// of the warp holds one - "while-while" - is 30 % slower here, because leaves are cheap (1.9
+// triangle tests per ray) compared with the descent they would make the other lanes wait for.)
+template <bool COUNT, bool VOLMESH>
+__device__ __forceinline__ bool trav_round(const rt_dev_scene& sc, Trav& T, float ray_t_min, float ray_t_max) {
   if (COUNT) T.cnt.rounds += 1;
   while (T.entry != RT_ENTRY_NONE && !(T.entry & RT_LEAF_FLAG)) trav_interior<COUNT>(sc, T);
-  if (T.entry != RT_ENTRY_NONE) trav_leaf<COUNT>(sc, T);
-  return T.entry == RT_ENTRY_NONE && !T.pop_next();
+  if (T.entry != RT_ENTRY_NONE) trav_leaf<COUNT, VOLMESH>(sc, T);
+  if (T.entry == RT_ENTRY_NONE) {
+    if (!T.pop_next<VOLMESH>()) return true;
+    if (VOLMESH && T.volret) volume_continue<COUNT>(sc, T, ray_t_min, ray_t_max);
+  }
+  return false;
 }
 
 // nearest RGB8 tap, texture.rs:28-31 (Q7)
@@ -744,10 +862,10 @@ __global__ void __launch_bounds__(RT_BLOCK) k_raygen(rt_frame fr, rt_ctrl* __res
 #define RT_FETCH_CHUNK 32  // measured: 32 -> 436 us, 64 -> 477 us, 256 -> 703 us per 2 M-ray iteration (load balance)
 #endif
 
-template <bool COUNT>
+template <bool COUNT, bool VOLMESH>
 __global__ void __launch_bounds__(RT_BLOCK, RT_EXTEND_MIN_BLOCKS) k_trace(rt_dev_scene sc, rt_frame fr, rt_ctrl* __restrict__ ctrl,
                                                                         rt_paths cur, rt_hits hits, const uint32_t* __restrict__ order) {
-  __shared__ __align__(8) uint32_t sstack[(RT_SMEM_STACK * (RT_STACK_DIST ? 2 : 1) + 6) * RT_BLOCK];
+  __shared__ __align__(8) uint32_t sstack[(RT_SMEM_STACK * (RT_STACK_DIST ? 2 : 1) + 6 + (VOLMESH ? 6 : 0)) * RT_BLOCK];
   const uint32_t n_rays = ctrl->n_rays;
   const uint32_t n_sorted = fr.sort_enabled ? ctrl->n_cont : 0u;  // continuing rays are visited in sorted order
   const uint32_t lane = threadIdx.x & 31u;
@@ -823,7 +941,7 @@ __global__ void __launch_bounds__(RT_BLOCK, RT_EXTEND_MIN_BLOCKS) k_trace(rt_dev
     // ---- traverse until enough lanes are idle again (or nothing is left to fetch)
     const bool can_refill = !(exhausted && c_next >= c_end);
     for (;;) {
-      if (have && !fin) fin = trav_round<COUNT>(sc, T);
+      if (have && !fin) fin = trav_round<COUNT, VOLMESH>(sc, T, fr.t_min, fr.t_max);
       uint32_t run = __ballot_sync(FULL, have && !fin);
       if (run == 0) break;
       if (can_refill && 32 - __popc(run) >= RT_REFILL_MIN) break;
@@ -1322,7 +1440,7 @@ void launch_advance(rt_ctrl* ctrl, uint32_t capacity, cudaStream_t st) {
 }
 int trace_blocks_per_sm() {
   int n = 0;
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_trace<false>, RT_BLOCK, 0);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_trace<false, false>, RT_BLOCK, 0);
   return n > 0 ? n : 1;
 }
 void launch_raygen(const rt_frame& fr, rt_ctrl* ctrl, rt_paths cur, cudaStream_t st) {
@@ -1332,8 +1450,13 @@ void launch_trace(const rt_dev_scene& sc, const rt_frame& fr, rt_ctrl* ctrl, rt_
                   bool count, uint32_t persistent_blocks, cudaStream_t st) {
   uint32_t full = (fr.capacity + RT_BLOCK - 1) / RT_BLOCK;
   uint32_t grid = full < persistent_blocks ? full : persistent_blocks;  // never more blocks than there could be rays
-  if (count) k_trace<true><<<grid, RT_BLOCK, 0, st>>>(sc, fr, ctrl, cur, hits, sort.order);
-  else k_trace<false><<<grid, RT_BLOCK, 0, st>>>(sc, fr, ctrl, cur, hits, sort.order);
+  if (sc.n_volume_meshes) {  // the variant that can nest boundary queries (a few more registers)
+    if (count) k_trace<true, true><<<grid, RT_BLOCK, 0, st>>>(sc, fr, ctrl, cur, hits, sort.order);
+    else k_trace<false, true><<<grid, RT_BLOCK, 0, st>>>(sc, fr, ctrl, cur, hits, sort.order);
+  } else {
+    if (count) k_trace<true, false><<<grid, RT_BLOCK, 0, st>>>(sc, fr, ctrl, cur, hits, sort.order);
+    else k_trace<false, false><<<grid, RT_BLOCK, 0, st>>>(sc, fr, ctrl, cur, hits, sort.order);
+  }
 }
 void launch_raysort(const rt_frame& fr, rt_ctrl* ctrl, rt_sortbuf sort, cudaStream_t st) {
   if (!fr.sort_enabled) return;

@@ -554,6 +554,7 @@ int lower_scene(const std::vector<HostTexture>& textures, const std::vector<rt_m
     BPrim p;
     bool bounded = true;
     switch (o.kind) {
+      case RT_OBJ_VOLUME_MESH:
       case RT_OBJ_MESH: {
         if (o.mesh < 0 || o.mesh >= (int)meshes.size()) {
           err = "instance references a mesh id that does not exist";
@@ -587,6 +588,10 @@ int lower_scene(const std::vector<HostTexture>& textures, const std::vector<rt_m
         q[8].i[1] = o.tex[3];
         q[8].i[2] = o.tex[4];
         q[8].i[3] = 0;
+        if (o.kind == RT_OBJ_VOLUME_MESH) {
+          q[9].f[0] = o.density;
+          q[9].i[1] = nvol++;
+        }
         if (m.n_reachable == 0) {
           bounded = false;  // nothing to hit: not in the TLAS, not in the plane list either
           break;
@@ -655,7 +660,7 @@ int lower_scene(const std::vector<HostTexture>& textures, const std::vector<rt_m
       for (int k = 0; k < 3; ++k) finite = finite && std::isfinite(p.mn[k]) && std::isfinite(p.mx[k]);
       if (!finite) {
         // cannot be bounded (e.g. NaN transform): test it for every ray instead
-        if (o.kind != RT_OBJ_MESH) L.planes.push_back((int32_t)oi);
+        if (o.kind != RT_OBJ_MESH && o.kind != RT_OBJ_VOLUME_MESH) L.planes.push_back((int32_t)oi);
         continue;
       }
       float amax = 0.0f;
@@ -667,7 +672,7 @@ int lower_scene(const std::vector<HostTexture>& textures, const std::vector<rt_m
         p.c[k] = 0.5f * (p.mn[k] + p.mx[k]);
       }
       p.id = (uint32_t)oi;
-      p.solo = o.kind == RT_OBJ_MESH ? 1u : 0u;
+      p.solo = (o.kind == RT_OBJ_MESH || o.kind == RT_OBJ_VOLUME_MESH) ? 1u : 0u;
       tprims.push_back(p);
     }
   }
@@ -708,7 +713,7 @@ int lower_scene(const std::vector<HostTexture>& textures, const std::vector<rt_m
     // TLAS depth + one RESTORE marker + the deepest BLAS
     uint32_t deepest = 0;
     for (const HostObject& o : objects)
-      if (o.kind == RT_OBJ_MESH) deepest = std::max(deepest, meshes[o.mesh].depth);
+      if (o.kind == RT_OBJ_MESH || o.kind == RT_OBJ_VOLUME_MESH) deepest = std::max(deepest, meshes[o.mesh].depth);
     if (L.tlas_depth + 1 + deepest > 62) {
       err = "BVH too deep for the traversal stack (" + std::to_string(L.tlas_depth + 1 + deepest) + " > 62)";
       return RT_ERR_UNSUPPORTED;

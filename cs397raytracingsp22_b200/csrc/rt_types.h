@@ -30,10 +30,12 @@
 #define RT_LEAF_FLAG 0x80000000u
 #define RT_ENTRY_NONE 0xFFFFFFFFu
 #define RT_ENTRY_RESTORE 0xFFFFFFFEu
+#define RT_ENTRY_VOLRET 0xFFFFFFFDu  /* end of a boundary query of a mesh-bounded volume */
 #define RT_SORT_BINS 262144u  /* 15-bit spatial hash of the origin cell << 3 | direction octant */
 #define RT_MAX_LEAF_TRIS 8  /* fits the 4-bit count of a packed stack entry */
 
-enum rt_obj_kind { RT_OBJ_MESH = 0, RT_OBJ_SPHERE = 1, RT_OBJ_TRIANGLE = 2, RT_OBJ_PLANE = 3, RT_OBJ_VOLUME = 4 };
+enum rt_obj_kind { RT_OBJ_MESH = 0, RT_OBJ_SPHERE = 1, RT_OBJ_TRIANGLE = 2, RT_OBJ_PLANE = 3, RT_OBJ_VOLUME = 4,
+                   RT_OBJ_VOLUME_MESH = 5 };
 
 // shade classes: the material tag, plus one class for texture-driven mesh hits
 enum { RT_CLASS_LAMBERT = 0, RT_CLASS_METAL = 1, RT_CLASS_DIELECTRIC = 2, RT_CLASS_PARAM = 3,
@@ -47,6 +49,7 @@ enum { RT_CLASS_LAMBERT = 0, RT_CLASS_METAL = 1, RT_CLASS_DIELECTRIC = 2, RT_CLA
 //   TRIANGLE q1 = (a.xyz, e1.x) q2 = (e1.yz, e2.xy) q3 = (e2.z, n.xyz)   n = normalize(e1 x e2)
 //   PLANE    q1 = (point.xyz, _) q2 = (normal.xyz, _)
 //   VOLUME   q1 = (center.xyz, radius) q2 = (density, vol_index(int), _, _)
+//   VOLUME_MESH  like MESH (q1..q3 inverse transform, q7.x BLAS root) + q9 = (density, vol_index(int), _, _)
 
 struct rt_dev_scene {
   const void* nodes;     // float4*
@@ -63,6 +66,7 @@ struct rt_dev_scene {
   uint32_t n_planes;
   uint32_t n_objects;
   uint32_t n_volumes;
+  uint32_t n_volume_meshes;  // > 0 selects the k_trace variant that can run boundary queries
   float tlas_min[3];     // root box of the TLAS
   float tlas_max[3];
 };

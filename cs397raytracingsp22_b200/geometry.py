@@ -50,16 +50,20 @@ class Plane:
 
 @dataclass(eq=False)
 class ConvexVolume:
-    boundary: object        # only a Sphere boundary is on the GPU path (SURVEY.md §8 f.1 is "next")
+    boundary: object        # a Sphere or a StaticMesh; other Intersectables can never give an exit hit (geometry.rs:508-509)
     phase_function: object
     density: float
 
     def lower(self, b, ctx) -> int:
-        if not isinstance(self.boundary, Sphere):
-            raise _ffi.RtError(_ffi.RT_ERR_UNSUPPORTED, "ConvexVolume: only a Sphere boundary is supported")
-        # the boundary's own material is ignored by the reference as well (geometry.rs:505-510)
-        return b.add_volume_sphere(self.boundary.center, self.boundary.radius, self.density,
-                                   ctx.material(self.phase_function))
+        # the boundary's own material / textures are ignored by the reference as well (geometry.rs:505-510)
+        if isinstance(self.boundary, Sphere):
+            return b.add_volume_sphere(self.boundary.center, self.boundary.radius, self.density,
+                                       ctx.material(self.phase_function))
+        if isinstance(self.boundary, StaticMesh):
+            m = self.boundary
+            return b.add_volume_mesh(ctx.mesh(m.mesh), cgmath.colmajor(m.transform), cgmath.colmajor(m.inv_transform),
+                                     self.density, ctx.material(self.phase_function))
+        raise _ffi.RtError(_ffi.RT_ERR_UNSUPPORTED, "ConvexVolume: the boundary must be a Sphere or a StaticMesh")
 
 
 class MeshData:

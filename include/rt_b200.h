@@ -166,6 +166,12 @@ int rt_add_plane(rt_scene* s, const float point[3], const float normal[3], int m
 int rt_add_volume_sphere(rt_scene* s, const float center[3], float radius, float density,
                          int phase_material);
 
+/* ConvexVolume with a StaticMesh boundary (geometry.rs:495-526 with boundary = a StaticMesh, geometry.rs:300-314):
+ * entry = the boundary's closest hit over all t, exit = its closest hit beyond entry + 1e-4.  The boundary's own
+ * material and textures are ignored, as in the reference.  xform / inv_xform as for rt_add_instance. */
+int rt_add_volume_mesh(rt_scene* s, int mesh, const float xform[16], const float* inv_xform, float density,
+                       int phase_material);
+
 /* Lower the scene (reachability mask, binned-SAH BLAS/TLAS, tables) and upload it to
  * CUDA device `device`.  May be called again after more rt_add_* calls. */
 int rt_commit(rt_scene* s, int device);

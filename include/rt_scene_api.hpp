@@ -186,14 +186,15 @@ struct Plane : Intersectable {  // geometry.rs:468-472
   Plane(Vec3 p, Vec3 n, MaterialRef m) : point(p), normal(n), material(std::move(m)) {}
   int lower(LowerCtx& c) const override { return check(rt_add_plane(c.s, &point.x, &normal.x, c.material(material))); }
 };
-struct ConvexVolume : Intersectable {  // geometry.rs:495-500; Sphere boundary only
+struct StaticMesh;
+struct ConvexVolume : Intersectable {  // geometry.rs:495-500; the boundary is a Sphere or a StaticMesh
   std::shared_ptr<const Sphere> boundary;
+  std::shared_ptr<const StaticMesh> mesh_boundary;
   MaterialRef phase_function;
   float density;
   ConvexVolume(std::shared_ptr<const Sphere> b, MaterialRef p, float d) : boundary(std::move(b)), phase_function(std::move(p)), density(d) {}
-  int lower(LowerCtx& c) const override {
-    return check(rt_add_volume_sphere(c.s, &boundary->center.x, boundary->radius, density, c.material(phase_function)));
-  }
+  ConvexVolume(std::shared_ptr<const StaticMesh> b, MaterialRef p, float d) : mesh_boundary(std::move(b)), phase_function(std::move(p)), density(d) {}
+  int lower(LowerCtx& c) const override;
 };
 struct MeshData {  // tobj::Mesh
   std::vector<float> positions, normals, texcoords;
@@ -242,6 +243,17 @@ struct StaticMesh : Intersectable {  // geometry.rs:127-134
     return check(rt_add_instance(c.s, mid, transform.m, nullptr, material ? c.material(material) : -1, tex));
   }
 };
+
+inline int ConvexVolume::lower(LowerCtx& c) const {
+  if (boundary) return check(rt_add_volume_sphere(c.s, &boundary->center.x, boundary->radius, density, c.material(phase_function)));
+  const StaticMesh& m = *mesh_boundary;
+  auto it = c.meshes.find(m.mesh.get());
+  int mid = it != c.meshes.end() ? it->second
+                                 : (c.meshes[m.mesh.get()] = check(rt_add_mesh(c.s, m.mesh->positions.data(), m.mesh->normals.data(),
+                                                                                m.mesh->texcoords.data(), (uint32_t)(m.mesh->positions.size() / 3),
+                                                                                m.mesh->indices.data(), (uint32_t)(m.mesh->indices.size() / 3))));
+  return check(rt_add_volume_mesh(c.s, mid, m.transform.m, nullptr, density, c.material(phase_function)));
+}
 
 // ---- camera and scene (tracing.rs)
 enum class CameraProjectionMode { Orthographic = RT_PROJ_ORTHOGRAPHIC, Perspective = RT_PROJ_PERSPECTIVE };

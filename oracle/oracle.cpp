@@ -373,6 +373,7 @@ struct Object {
   float radius = 0.0f;
   float density = 0.0f;
   int vol_index = -1;  // ordinal among volumes (RNG contract)
+  bool mesh_boundary = false;  // ConvexVolume whose boundary is a StaticMesh (mesh / transform fields above)
 };
 
 }  // namespace
@@ -464,6 +465,13 @@ inline bool volume_hit(const Object& o, const Ray& ray, float t_min, float t_max
   return false;
 }
 
+// the `distance` of StaticMesh::intersect_ray (geometry.rs:301-314) for an arbitrary t-range; the hit frame and the
+// material are not needed by ConvexVolume, which only reads `.distance` (geometry.rs:507,510)
+bool brute_mesh_hit(const Mesh& m, const std::vector<uint8_t>& reach, const Ray& ray, float t_min, float t_max, Hit& out,
+                    Counters* cnt);
+inline bool boundary_mesh_distance(const orc_scene& sc, const Object& o, const Ray& ray, float t_min, float t_max, int mode,
+                                   float& distance);
+
 // StaticMesh::get_adjusted_normal, geometry.rs:274-298
 inline V3 adjusted_normal(const orc_scene& sc, const Object& o, const Hit& hit) {
   V3 n = hit.normal;
@@ -499,8 +507,8 @@ inline void material_at_uv(const orc_scene& sc, const Object& o, Hit& hit) {
 // brute-force stand-in for the tree: every reachable triangle with the same [t_min,t_max];
 // keep the smallest t, and among equal t the highest index (what left-then-right with
 // t_max = best_t and inclusive bounds produces, geometry.rs:105-115,349)
-inline bool brute_mesh_hit(const Mesh& m, const std::vector<uint8_t>& reach, const Ray& ray, float t_min,
-                           float t_max, Hit& out, Counters* cnt) {
+bool brute_mesh_hit(const Mesh& m, const std::vector<uint8_t>& reach, const Ray& ray, float t_min, float t_max, Hit& out,
+                    Counters* cnt) {
   bool have = false;
   float best = t_max;
   for (uint32_t t = 0; t < m.ntris(); ++t) {
@@ -536,6 +544,39 @@ inline bool mesh_hit(const orc_scene& sc, const Object& o, int obj_index, const 
   return true;
 }
 
+inline bool boundary_mesh_distance(const orc_scene& sc, const Object& o, const Ray& ray, float t_min, float t_max, int mode,
+                                   float& distance) {
+  const Mesh& m = *sc.meshes[o.mesh];
+  if (m.root < 0) return false;
+  Ray tr;
+  tr.origin = transform_point(o.inv_transform, ray.origin);
+  tr.direction = transform_vector(o.inv_transform, ray.direction);
+  Hit h;
+  bool ok = mode == MODE_REF_TREE ? bvh_hit(m, m.root, tr, t_min, t_max, h, nullptr)
+                                  : brute_mesh_hit(m, sc.reach[o.mesh], tr, t_min, t_max, h, nullptr);
+  if (ok) distance = h.distance;
+  return ok;
+}
+// ConvexVolume::intersect_ray with a StaticMesh boundary, geometry.rs:502-526
+inline bool volume_mesh_hit(const orc_scene& sc, const Object& o, const Ray& ray, float t_min, float t_max, int mode,
+                            const RngKey& key, uint32_t bounce, Hit& out) {
+  float t_entr, t_exit;
+  if (!boundary_mesh_distance(sc, o, ray, -FLT_MAX, FLT_MAX, mode, t_entr)) return false;
+  if (!boundary_mesh_distance(sc, o, ray, t_entr + 0.0001f, FLT_MAX, mode, t_exit)) return false;
+  if (t_exit < t_min || t_entr > t_max) return false;
+  float t_start = rmax(t_entr, t_min);
+  float t_end = rmin(t_exit, t_max);
+  float dist_in_volume = t_end - t_start;
+  U4 r = draw(key, bounce, 1u + (uint32_t)o.vol_index / 4u);
+  float U = u01(r.v[o.vol_index & 3]);
+  float dist_before_scatter = (-1.0f / o.density) * std::log(U);
+  if (dist_before_scatter < dist_in_volume) {
+    out = make_hit(t_start + dist_before_scatter, v3(0, 0, 0), o.material, ray);
+    return true;
+  }
+  return false;
+}
+
 // Scene::intersect_ray, tracing.rs:327-346
 bool scene_hit(const orc_scene& sc, const Ray& ray, float t_min, float t_max, int mode, const RngKey& key,
                uint32_t bounce, Hit& best, Counters* cnt) {
@@ -550,7 +591,10 @@ bool scene_hit(const orc_scene& sc, const Ray& ray, float t_min, float t_max, in
       case OBJ_SPHERE: ok = sphere_hit(o.a, o.radius, o.material, ray, t_min, t_max, h); break;
       case OBJ_TRIANGLE: ok = triangle_hit(o, ray, t_min, t_max, h); break;
       case OBJ_PLANE: ok = plane_hit(o, ray, t_min, t_max, h); break;
-      case OBJ_VOLUME: ok = volume_hit(o, ray, t_min, t_max, key, bounce, h); break;
+      case OBJ_VOLUME:
+        ok = o.mesh_boundary ? volume_mesh_hit(sc, o, ray, t_min, t_max, mode, key, bounce, h)
+                             : volume_hit(o, ray, t_min, t_max, key, bounce, h);
+        break;
     }
     if (!ok) continue;
     h.obj = (int)i;
@@ -874,6 +918,22 @@ int orc_add_volume_sphere(orc_scene* s, const float c[3], float radius, float de
   o.kind = OBJ_VOLUME;
   o.a = v3(c[0], c[1], c[2]);
   o.radius = radius;
+  o.density = density;
+  o.material = phase_material;
+  o.vol_index = s->n_volumes++;
+  s->objects.push_back(o);
+  return (int)s->objects.size() - 1;
+}
+
+int orc_add_volume_mesh(orc_scene* s, int mesh, const float xform[16], const float inv_xform[16], float density,
+                        int phase_material) {
+  if (!s || mesh < 0 || mesh >= (int)s->meshes.size() || !xform || !inv_xform) return RT_ERR_INVALID;
+  Object o;
+  o.kind = OBJ_VOLUME;
+  o.mesh_boundary = true;
+  o.mesh = mesh;
+  std::memcpy(o.transform.m, xform, 64);
+  std::memcpy(o.inv_transform.m, inv_xform, 64);
   o.density = density;
   o.material = phase_material;
   o.vol_index = s->n_volumes++;

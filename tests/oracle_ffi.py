@@ -59,6 +59,7 @@ def load():
         "orc_add_triangle": (C.c_int, [_P, _F, _F, _F, C.c_int]),
         "orc_add_plane": (C.c_int, [_P, _F, _F, C.c_int]),
         "orc_add_volume_sphere": (C.c_int, [_P, _F, C.c_float, C.c_float, C.c_int]),
+        "orc_add_volume_mesh": (C.c_int, [_P, C.c_int, _F, _F, C.c_float, C.c_int]),
         "orc_render": (C.c_int, [_P, cam, C.c_uint64, C.c_int, C.c_uint32, C.c_uint32, C.c_int, _F, _U8, st]),
         "orc_trace_primary": (C.c_int, [_P, cam, C.c_uint64, C.c_int, C.c_uint32, _I, _I, _F, _F, _F]),
         "orc_intersect_rays": (C.c_int, [_P, C.c_uint64, C.c_int, C.c_uint32, _F, C.c_float, C.c_float, _I, _I, _F,
@@ -144,6 +145,11 @@ class OracleBackend:
     def add_volume_sphere(self, center, radius, density, material) -> int:
         return _check(self.lib.orc_add_volume_sphere(self.handle, _ffi.fptr(_ffi.f3(center)), float(radius),
                                                      float(density), material))
+
+    def add_volume_mesh(self, mesh, xform_colmajor, inv_colmajor, density, material) -> int:
+        x = np.ascontiguousarray(xform_colmajor, dtype=np.float32).reshape(16)
+        inv = np.ascontiguousarray(inv_colmajor, dtype=np.float32).reshape(16)
+        return _check(self.lib.orc_add_volume_mesh(self.handle, mesh, _ffi.fptr(x), _ffi.fptr(inv), float(density), material))
 
     def commit(self, device: int = 0):
         pass

@@ -222,6 +222,66 @@ def test_volume_transmittance_on_the_gpu(gpu):
     assert np.all(a["normal"][both] == 0.0) and np.all(a["frontface"][both] == 0)
 
 
+def _foggy_scene(width=96, height=72, spp=16):
+    """Two mesh-bounded volumes (a rotated cube of fog with a metal ball inside it, a teapot-shaped absorbing cloud), a
+    sphere-bounded one, a floor and a light: every kind of volume boundary in one frame."""
+    from cs397raytracingsp22_b200 import cgmath as cg, scenes
+    cube = rt.StaticMesh.load_from_file(scenes.obj_path("cube"), material=rt.Lambertian(),
+                                        transform=cg.chain(cg.from_translation((-1.2, 1.0, 1.0)), cg.from_angle_y(30.0), cg.from_scale(0.9)))
+    teapot = rt.StaticMesh.load_from_file(scenes.obj_path("teapot"), material=rt.Lambertian(),
+                                          transform=cg.chain(cg.from_translation((1.4, 0.8, 1.2)), cg.from_angle_x(-90.0), cg.from_scale(1.6)))
+    light = rt.Lambertian(albedo=(0, 0.6, 0), emission=(7, 7, 7))
+    objs = [
+        rt.ConvexVolume(boundary=cube, phase_function=rt.Isotropic(albedo=(0.9, 0.9, 1.0)), density=1.5),
+        rt.Sphere((-1.2, 1.0, 1.0), 0.35, rt.Metal(albedo=(0.9, 0.7, 0.3), roughness=0.1)),
+        rt.ConvexVolume(boundary=teapot, phase_function=rt.Isotropic(albedo=(0.2, 0.2, 0.2)), density=3.0),
+        rt.ConvexVolume(boundary=rt.Sphere((0.1, 2.4, 0.0), 0.6, rt.Dielectric(1.5)), phase_function=rt.Isotropic(), density=2.0),
+        rt.Plane((0, 0, 0), (0, 1, 0), rt.Lambertian(albedo=(0.5, 0.5, 0.5))),
+        rt.Triangle((-2.5, 5, -0.5), (2.5, 5, -0.5), (2.5, 5, 3.5), light),
+        rt.Triangle((-2.5, 5, -0.5), (-2.5, 5, 3.5), (2.5, 5, 3.5), light),
+    ]
+    cam = rt.Camera(screen_width=width, screen_height=height, aa_sample_count=spp, path_depth=8)
+    return rt.Scene(camera=cam, objects=objs)
+
+
+def test_mesh_bounded_volumes(gpu):
+    """ConvexVolume with a StaticMesh boundary, against the reference-tree oracle: the same rays
+    scatter in the same volumes at the same distance (keyed draws), from outside and from inside the boundary, and
+    the rendered image tracks the oracle sample for sample."""
+    sc = _foggy_scene()
+    g, o = _both(sc)
+    cam = sc.camera.to_c()
+    assert g.lower_info()["objects"] == 7
+    vols = _volume_ids(sc)
+    assert vols == [0, 2, 3]
+    a = g.trace_primary(cam, SEED, 3)
+    b = o.trace_primary(cam, SEED, 3, mode=O.MODE_REF_TREE)
+    assert np.array_equal(a["ray"], b["ray"])
+    assert (a["obj"] == b["obj"]).mean() > 0.9995            # an ulp of logf can move a scatter point past the exit
+    same = a["obj"] == b["obj"]
+    hit = same & (b["obj"] >= 0)
+    assert np.abs(a["t"][hit] - b["t"][hit]).max() < 1e-4
+    for v in vols:
+        assert (b["obj"] == v).sum() > 20, f"volume {v} is never hit: the scene does not test it"
+    # rays that start inside the fog cube / the cloud, un-normalised directions
+    rng = np.random.RandomState(4)
+    n = 20000
+    org = np.where(rng.rand(n, 1) < 0.5, np.array([[-1.2, 1.0, 1.0]]) + rng.uniform(-0.5, 0.5, (n, 3)),
+                   np.array([[1.4, 0.9, 1.2]]) + rng.uniform(-0.4, 0.4, (n, 3)))
+    rays = np.concatenate([org, rng.uniform(-1, 1, (n, 3))], axis=1).astype(np.float32)
+    ra = g.intersect_rays(rays, 0.001, 100.0, seed=21)
+    rb = o.intersect_rays(rays, 0.001, 100.0, seed=21, mode=O.MODE_REF_TREE)
+    assert (ra["obj"] == rb["obj"]).mean() > 0.9995
+    both = (ra["obj"] == rb["obj"]) & (rb["obj"] >= 0)
+    assert np.abs(ra["t"][both] - rb["t"][both]).max() < 1e-4
+    assert np.isin(rb["obj"], vols).mean() > 0.3
+    lin_g, rgb_g, st_g, lin_o, rgb_o, st_o = _render_pair(sc)
+    diff = np.abs(lin_g - lin_o)
+    assert np.median(diff) <= 1e-5
+    assert (diff.max(axis=2) > 1e-3 * np.maximum(lin_o.max(axis=2), float(lin_o.mean()))).mean() < 0.05
+    assert abs(float(lin_g.mean()) - float(lin_o.mean())) <= 3e-3 * float(lin_o.mean())
+
+
 def test_nan_sample_poisons_only_its_pixel_like_the_reference(gpu):
     """Q12: a NaN radiance sample makes the reference's pixel mean NaN, which `as u8` turns into 0."""
     # a degenerate loose triangle (zero area) has a NaN normal -> NaN scatter direction -> NaN throughput

@@ -98,6 +98,28 @@ def test_volume_transmittance():
     assert abs(p2 - (1 - math.exp(-1 * r * sigma))) < 4e-3
 
 
+def test_mesh_bounded_volume_transmittance():
+    """ConvexVolume with a StaticMesh boundary.  A ray through a cube of side 2 scatters with
+    probability 1-exp(-2 s); entry / exit come from the mesh BVH queried over all t, so a ray starting INSIDE sees the
+    negative entry distance and only the part ahead of it."""
+    sigma = 0.6
+    cube = rt.StaticMesh.load_from_file(scenes.obj_path("cube"), material=rt.Lambertian())
+    vol = rt.ConvexVolume(boundary=cube, phase_function=rt.Isotropic(albedo=(1, 1, 1)), density=sigma)
+    b = O.lower_to_oracle(rt.Scene(camera=rt.Camera(), objects=[vol]))
+    n = 200_000
+    outside = np.tile(np.array([0.3, 0.2, 5, 0, 0, -1], np.float32), (n, 1))
+    inside = np.tile(np.array([0.3, 0.2, 0.5, 0, 0, -1], np.float32), (n, 1))     # 1.5 units of fog ahead
+    for mode in (O.MODE_REF_TREE, O.MODE_BRUTE):
+        r = b.intersect_rays(outside, 0.001, 100.0, seed=11, mode=mode)
+        assert abs((r["obj"] == 0).mean() - (1 - math.exp(-2 * sigma))) < 4e-3
+        hit = r["obj"] == 0
+        assert r["t"][hit].min() >= 4.0 - 1e-4 and r["t"][hit].max() <= 6.0 + 1e-4
+        assert np.all(r["normal"][hit] == 0.0) and np.all(r["frontface"][hit] == 0)
+        r = b.intersect_rays(inside, 0.001, 100.0, seed=12, mode=mode)
+        assert abs((r["obj"] == 0).mean() - (1 - math.exp(-1.5 * sigma))) < 4e-3
+        assert r["t"][r["obj"] == 0].max() <= 1.5 + 1e-4
+
+
 def test_pixel_filter_footprint():
     """Multi-jitter offsets span [-1, 1) pixel with mean -(1/(2 sqrt n) + 1/(2n)) (SURVEY.md §4 KAT 3, Q8)."""
     cam = rt.Camera(screen_width=32, screen_height=32, aa_sample_count=64).to_c()
