@@ -596,18 +596,32 @@ int lower_scene(const std::vector<HostTexture>& textures, const std::vector<rt_m
           bounded = false;  // nothing to hit: not in the TLAS, not in the plane list either
           break;
         }
-        // world box = box of the 8 transformed corners of the (padded) object-space root box
+        // world box = box of the transformed vertices of the reachable triangles (a rotated instance gets a much
+        // tighter box than the box of its object-space box's corners would), grown by the object-space padding
+        // pushed through the linear part of the transform
         for (int k = 0; k < 3; ++k) {
           p.mn[k] = FLT_MAX;
           p.mx[k] = -FLT_MAX;
         }
-        for (int corner = 0; corner < 8; ++corner) {
-          float v[3] = {(corner & 1) ? m.root_max[0] : m.root_min[0], (corner & 2) ? m.root_max[1] : m.root_min[1],
-                        (corner & 4) ? m.root_max[2] : m.root_min[2]};
+        for (uint32_t t = 0; t < m.ntris(); ++t) {
+          if (!m.reach[t]) continue;
+          for (int c = 0; c < 3; ++c) {
+            const float* v = &m.pos[3 * (size_t)m.idx[3 * t + c]];
+            for (int k = 0; k < 3; ++k) {
+              float w = o.xform[k] * v[0] + o.xform[4 + k] * v[1] + o.xform[8 + k] * v[2] + o.xform[12 + k];
+              p.mn[k] = std::min(p.mn[k], w);
+              p.mx[k] = std::max(p.mx[k], w);
+            }
+          }
+        }
+        {
+          float amax_obj = 0.0f;
+          for (int k = 0; k < 3; ++k) amax_obj = std::max(amax_obj, std::max(std::fabs(m.root_min[k]), std::fabs(m.root_max[k])));
+          float pad_obj = 8e-6f * amax_obj;
           for (int k = 0; k < 3; ++k) {
-            float w = o.xform[k] * v[0] + o.xform[4 + k] * v[1] + o.xform[8 + k] * v[2] + o.xform[12 + k];
-            p.mn[k] = std::min(p.mn[k], w);
-            p.mx[k] = std::max(p.mx[k], w);
+            float g = (std::fabs(o.xform[k]) + std::fabs(o.xform[4 + k]) + std::fabs(o.xform[8 + k])) * pad_obj;
+            p.mn[k] -= g;
+            p.mx[k] += g;
           }
         }
         break;
