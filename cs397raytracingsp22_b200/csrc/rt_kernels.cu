@@ -142,7 +142,8 @@ __device__ __forceinline__ void camera_ray(const rt_frame& fr, uint32_t x, uint3
   f3 center = mk(ps * ((float)x - 0.5f * (float)fr.width + 0.5f) + off_x,
                  ps * (0.5f + 0.5f * (float)fr.height - (float)y) + off_y, -fr.focal_length);
   f3 focus = normalize(center) * fr.focus_dist;
-  f3 lens = fr.lens_radius * disk_from(r.z, r.w);
+  // lens_radius == 0: 0 * disk is (+-0, +-0, 0) and changes nothing below, so the sin/cos are skipped
+  f3 lens = fr.lens_radius != 0.0f ? fr.lens_radius * disk_from(r.z, r.w) : mk(0.0f, 0.0f, 0.0f);
   f3 dcam = normalize(focus - lens);
   f3 c0 = mk(fr.rot0[0], fr.rot0[1], fr.rot0[2]), c1 = mk(fr.rot1[0], fr.rot1[1], fr.rot1[2]),
      c2 = mk(fr.rot2[0], fr.rot2[1], fr.rot2[2]);
