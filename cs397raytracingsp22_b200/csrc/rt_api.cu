@@ -724,7 +724,9 @@ int rt_render_accum(rt_scene* s, const rt_camera* cam, const rt_render_opts* opt
   if (stats) std::memset(stats, 0, sizeof *stats);
   if (total == 0) return RT_OK;
   if ((rc = ensure_runtime(s)) != RT_OK) return rc;
-  cudaStream_t st = stream ? (cudaStream_t)stream : s->own_stream;
+  // NULL means the (legacy) default stream, as documented: work must be ordered after whatever the caller has
+  // already enqueued there (e.g. the memset of d_accum), which a private non-blocking stream would not be
+  cudaStream_t st = (cudaStream_t)stream;
   // Secondary-ray sorting (k_shade keys -> k_raysort_*).  It pays where traversal dominates: on C4 k_trace drops from
   // 1230 to 990 us per 8 Mi rays for ~150 us of sorting (+9 %); on C2 (two 240-triangle teapots in a closed box, 5 nodes
   // per ray) the indirection costs more than it saves (-14 %).  Hence the switch on the amount of instanced geometry.

@@ -1,5 +1,6 @@
 """A/B helper (development only): run bench.py once per (library variant, env knobs) and print one line each.
-usage: tools_ab.py [lib.so ...] [-- KEY=VAL,KEY=VAL ...]"""
+Variants are built with `python cs397raytracingsp22_b200/build.py -DNAME=VALUE --out=build/rt_x.so`.
+usage (from the repo root): python tools/ab.py [lib.so ...] [-- KEY=VAL,KEY=VAL ...]"""
 import glob, json, os, subprocess, sys
 args = sys.argv[1:]
 envsets = [""]
