@@ -427,11 +427,13 @@ void build_mesh(HostMesh& m) {
   // triangle the reference's Möller–Trumbore test accepts is never culled by rounding in the
   // slab test (flat boxes of coplanar triangles get thickness this way, cf. Q3).
   m.depth = prims.empty() ? 0 : bvh_depth(nodes);
-  float pad = 4e-6f * amax + 1e-30f;
-  nodes_to_quads(nodes, pad, m.nodes);
+  // the padding itself is applied when the scene is lowered, because it depends on how the mesh is instanced
+  m.pad_base = 4e-6f * amax + 1e-30f;
+  m.amax = amax;
+  nodes_to_quads(nodes, 0.0f, m.nodes);
   for (int k = 0; k < 3; ++k) {
-    m.root_min[k] = prims.empty() ? 0.0f : nodes[0].mn[k] - pad;
-    m.root_max[k] = prims.empty() ? 0.0f : nodes[0].mx[k] + pad;
+    m.root_min[k] = prims.empty() ? 0.0f : nodes[0].mn[k];
+    m.root_max[k] = prims.empty() ? 0.0f : nodes[0].mx[k];
   }
   m.root_entry_local = prims.empty() ? RT_ENTRY_NONE : pack_entry(nodes[0].leftFirst, nodes[0].count);
 
@@ -487,8 +489,54 @@ int lower_scene(const std::vector<HostTexture>& textures, const std::vector<rt_m
   L = Lowered();
   // BLASes, concatenated; child and triangle indices rebased to the global arrays
   std::vector<uint32_t> node_base(meshes.size()), tri_base(meshes.size()), shade_base(meshes.size());
+  // Box padding per mesh.  The slab test's rounding error is a few ulps of the OBJECT-SPACE ray origin, which for a
+  // tiny instance in a big scene is far larger than the mesh itself (C5: drones scaled by 6e-4, origins 3e4 units
+  // away from a mesh of extent 500).  So the base padding (4e-6 of the largest coordinate) grows with the ratio of
+  // the scene's extent, measured in each instance's object units, to the mesh's own extent.
+  float world_mn[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, world_mx[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
+  for (const HostObject& o : objects) {
+    float c[3], r = 0.0f;
+    bool has = true;
+    if (o.kind == RT_OBJ_MESH || o.kind == RT_OBJ_VOLUME_MESH) {
+      if (o.mesh < 0 || o.mesh >= (int)meshes.size()) continue;
+      const HostMesh& m = meshes[o.mesh];
+      for (int k = 0; k < 3; ++k) c[k] = o.xform[12 + k];
+      float sc = 0.0f;
+      for (int k = 0; k < 9; ++k) sc = std::max(sc, std::fabs(o.xform[(k / 3) * 4 + k % 3]));
+      r = 1.8f * sc * m.amax;
+    } else if (o.kind == RT_OBJ_SPHERE || o.kind == RT_OBJ_VOLUME) {
+      for (int k = 0; k < 3; ++k) c[k] = o.a[k];
+      r = std::fabs(o.radius);
+    } else if (o.kind == RT_OBJ_TRIANGLE) {
+      for (int k = 0; k < 3; ++k) {
+        c[k] = o.a[k];
+        r = std::max(r, std::max(std::fabs(o.b[k] - o.a[k]), std::fabs(o.c[k] - o.a[k])));
+      }
+    } else {
+      has = false;
+    }
+    if (!has) continue;
+    for (int k = 0; k < 3; ++k) {
+      if (std::isfinite(c[k]) && std::isfinite(r)) {
+        world_mn[k] = std::min(world_mn[k], c[k] - r);
+        world_mx[k] = std::max(world_mx[k], c[k] + r);
+      }
+    }
+  }
+  float world_ext = 0.0f;
+  for (int k = 0; k < 3; ++k)
+    if (world_mx[k] >= world_mn[k]) world_ext = std::max(world_ext, world_mx[k] - world_mn[k]);
+  std::vector<float> pad_factor(meshes.size(), 1.0f);
+  for (const HostObject& o : objects) {
+    if ((o.kind != RT_OBJ_MESH && o.kind != RT_OBJ_VOLUME_MESH) || o.mesh < 0 || o.mesh >= (int)meshes.size()) continue;
+    float isc = 0.0f;  // largest entry of the inverse's linear part ~ object units per world unit
+    for (int k = 0; k < 9; ++k) isc = std::max(isc, std::fabs(o.inv_xform[(k / 3) * 4 + k % 3]));
+    float ratio = 2.0f * world_ext * isc / std::max(meshes[o.mesh].amax, 1e-30f);  // rays may start ~2 extents away
+    if (std::isfinite(ratio)) pad_factor[o.mesh] = std::max(pad_factor[o.mesh], std::min(ratio / 8.0f, 256.0f));
+  }
   for (size_t mi = 0; mi < meshes.size(); ++mi) {
     HostMesh& m = meshes[mi];
+    m.pad = m.pad_base * pad_factor[mi];
     node_base[mi] = (uint32_t)(L.nodes.size() / RT_NODE_QUADS);
     tri_base[mi] = (uint32_t)(L.tris.size() / RT_TRI_QUADS);
     shade_base[mi] = (uint32_t)(L.shade.size() / RT_SHADE_QUADS);
@@ -497,6 +545,10 @@ int lower_scene(const std::vector<HostTexture>& textures, const std::vector<rt_m
     for (size_t q = n0; q < L.nodes.size(); q += 2) {
       uint32_t count = L.nodes[q + 1].u[3];
       L.nodes[q].u[3] += count ? tri_base[mi] : node_base[mi];
+      for (int k = 0; k < 3; ++k) {
+        L.nodes[q].f[k] -= m.pad;
+        L.nodes[q + 1].f[k] += m.pad;
+      }
     }
     // guards: boxes and per-triangle index lists, rebased to the global arrays
     uint32_t guard_base = (uint32_t)(L.guards.size() / 2), glist_base = (uint32_t)L.guard_list.size();
@@ -617,7 +669,7 @@ int lower_scene(const std::vector<HostTexture>& textures, const std::vector<rt_m
         {
           float amax_obj = 0.0f;
           for (int k = 0; k < 3; ++k) amax_obj = std::max(amax_obj, std::max(std::fabs(m.root_min[k]), std::fabs(m.root_max[k])));
-          float pad_obj = 8e-6f * amax_obj;
+          float pad_obj = 2.0f * m.pad + 8e-6f * amax_obj;
           for (int k = 0; k < 3; ++k) {
             float g = (std::fabs(o.xform[k]) + std::fabs(o.xform[4 + k]) + std::fabs(o.xform[8 + k])) * pad_obj;
             p.mn[k] -= g;

@@ -41,6 +41,7 @@ struct HostMesh {
   uint32_t root_entry_local;   // packed entry of the root (local indices)
   uint32_t n_reachable;
   uint32_t depth = 0;          // longest root-to-leaf path of the BLAS, in nodes
+  float pad_base = 0, amax = 0, pad = 0;  // box padding: base (4e-6 of the largest coordinate), applied value
   uint32_t ntris() const { return (uint32_t)(idx.size() / 3); }
 };
 

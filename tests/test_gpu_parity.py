@@ -464,3 +464,25 @@ def test_full_resolution_c4_properties(gpu):
     b = o.trace_primary(cam, SEED, 777, mode=O.MODE_REF_TREE)
     assert np.array_equal(a["ray"], b["ray"])
     _assert_hits_match(a, b, "c4 full resolution", _volume_ids(sc))
+
+
+def test_tiny_instance_far_from_the_origin_of_its_rays(gpu):
+    """Conservative culling under stress: a teapot scaled by 2e-3 seen through a long lens, so object-space ray origins
+    are ~3000 mesh extents away and the slab tests run on heavily rounded numbers.  Whatever the reference's
+    arithmetic makes of such rays, the CUDA path must make the same of them: ids and distances exact."""
+    from cs397raytracingsp22_b200 import cgmath as cg, scenes
+    pot = rt.StaticMesh.load_from_file(scenes.obj_path("teapot"), material=rt.Metal(albedo=(0.9, 0.9, 0.9), roughness=0.0),
+                                       transform=cg.chain(cg.from_translation((0.0, 2.0, 0.0)), cg.from_angle_x(-90.0),
+                                                          cg.from_angle_y(20.0), cg.from_scale(2e-3)))
+    cam = rt.Camera(eyepoint=(0.0, 2.0, 5.5), screen_width=96, screen_height=96, aa_sample_count=4, path_depth=3,
+                    focal_length=900.0, focus_dist=5.5)
+    sc = rt.Scene(camera=cam, objects=[pot, rt.Plane((0, 0, 0), (0, 1, 0), rt.Lambertian())])
+    g, o = _both(sc)
+    for sample in range(4):
+        a = g.trace_primary(cam.to_c(), SEED, sample)
+        b = o.trace_primary(cam.to_c(), SEED, sample, mode=O.MODE_REF_TREE)
+        assert np.array_equal(a["ray"], b["ray"])
+        assert (b["obj"] == 0).sum() > 500, "the teapot is not in view: the test does not test anything"
+        assert np.array_equal(a["obj"], b["obj"]) and np.array_equal(a["prim"], b["prim"])
+        hit = b["obj"] >= 0
+        assert np.array_equal(a["t"][hit], b["t"][hit])
