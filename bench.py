@@ -45,6 +45,7 @@ def parse_args():
     ap.add_argument("--spp", type=int, default=0, help="override samples per pixel (invalidates the headline)")
     ap.add_argument("--width", type=int, default=0)
     ap.add_argument("--height", type=int, default=0)
+    ap.add_argument("--emulate-shards", type=int, default=0, help="diagnostics: render shard 0 of this many (with --shard)")
     ap.add_argument("--depth", type=int, default=0, help="override path_depth (diagnostics; invalidates the headline)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -232,6 +233,8 @@ def main():
     build_s = time.perf_counter() - t0
 
     def opts_for(flags=0):
+        if args.emulate_shards:
+            return D.shard_opts(0, args.emulate_shards, SEED, args.shard, wavefront=args.wavefront, flags=flags)
         if world == 1 or args.shard == "weak":
             return D.shard_opts(0, 1, SEED + (rank if args.shard == "weak" else 0), "all", wavefront=args.wavefront,
                                 flags=flags)

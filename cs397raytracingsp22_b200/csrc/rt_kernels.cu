@@ -156,7 +156,26 @@ __device__ __forceinline__ void camera_ray(const rt_frame& fr, uint32_t x, uint3
 __device__ __forceinline__ bool work_to_pixel(const rt_frame& fr, unsigned long long g, uint32_t& x, uint32_t& y,
                                               uint32_t& sample) {
   unsigned long long pl;
-  if (g < 0x100000000ull) {  // 32-bit division is several times cheaper and covers shards of up to 4 Gi paths
+  if (fr.sample_major == 2u) {
+    // groups of 32 sample indices: a warp is 32 consecutive samples of ONE pixel (as coherent as camera rays get), but
+    // consecutive warps walk the pixels, so the wavefront spans the whole shard instead of a few image rows
+    unsigned long long w = g >> 5;
+    unsigned long long q = w / fr.pixel_slots;
+    pl = w - q * fr.pixel_slots;
+    sample = fr.sample_begin + (uint32_t)q * 32u + (uint32_t)(g & 31ull);
+  } else if (fr.sample_major) {
+    // a warp is 32 neighbouring pixels at one sample index; the wavefront then spans the whole shard at a few
+    // sample indices instead of a few pixels at all of theirs
+    if (g < 0x100000000ull && fr.pixel_slots < 0x100000000ull) {
+      uint32_t q = (uint32_t)g / (uint32_t)fr.pixel_slots;
+      pl = (uint32_t)g - q * (uint32_t)fr.pixel_slots;
+      sample = fr.sample_begin + q;
+    } else {
+      unsigned long long q = g / fr.pixel_slots;
+      pl = g - q * fr.pixel_slots;
+      sample = fr.sample_begin + (uint32_t)q;
+    }
+  } else if (g < 0x100000000ull) {  // 32-bit division is several times cheaper and covers shards of up to 4 Gi paths
     uint32_t q = (uint32_t)g / fr.sample_count;
     pl = q;
     sample = fr.sample_begin + ((uint32_t)g - q * fr.sample_count);

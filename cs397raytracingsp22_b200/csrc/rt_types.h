@@ -102,6 +102,8 @@ struct rt_frame {
   // shard
   uint32_t shard_mode, shard_rank, shard_count, tile_size, tiles_x, tiles_y;
   uint32_t sample_begin, sample_count;
+  uint32_t sample_major;            // 1: consecutive work indices walk the pixels (sample index changes slowest)
+  unsigned long long pixel_slots;   // pixel slots of this shard (work items = pixel_slots * sample_count)
   uint32_t capacity;                // wavefront width P
   // secondary-ray sorting (k_shade -> k_raysort_*): origin cell (16^3 over the TLAS box, Morton order) | direction octant
   uint32_t sort_enabled;
