@@ -46,7 +46,8 @@ class rt_camera(C.Structure):
 class rt_render_opts(C.Structure):
     _fields_ = [("seed", C.c_uint64), ("shard_mode", C.c_uint32), ("shard_rank", C.c_uint32),
                 ("shard_count", C.c_uint32), ("tile_size", C.c_uint32), ("sample_begin", C.c_uint32),
-                ("sample_end", C.c_uint32), ("wavefront", C.c_uint32), ("flags", C.c_uint32)]
+                ("sample_end", C.c_uint32), ("wavefront", C.c_uint32), ("flags", C.c_uint32),
+                ("point_light_pos", C.c_float * 3), ("ambient", C.c_float * 3)]
 
 
 class rt_stats(C.Structure):

@@ -178,10 +178,10 @@ int ensure_wavefront(rt_scene* s, uint32_t capacity) { return ensure_lane(s, 0, 
 
 int check_camera(const rt_camera* cam) {
   if (!cam) return fail(RT_ERR_INVALID, "camera is NULL");
-  if (cam->projection_mode != RT_PROJ_PERSPECTIVE)
-    return fail(RT_ERR_UNSUPPORTED, "only CameraProjectionMode::Perspective is on the GPU path (tracing.rs:196-201)");
-  if (cam->shading_mode != RT_SHADE_PATHTRACE)
-    return fail(RT_ERR_UNSUPPORTED, "only ShadingMode::PathTrace is on the GPU path (tracing.rs:276)");
+  if (cam->projection_mode != RT_PROJ_PERSPECTIVE && cam->projection_mode != RT_PROJ_ORTHOGRAPHIC)
+    return fail(RT_ERR_INVALID, "unknown CameraProjectionMode (tracing.rs:25-28)");
+  if (cam->shading_mode != RT_SHADE_PATHTRACE && cam->shading_mode != RT_SHADE_PHONG)
+    return fail(RT_ERR_INVALID, "unknown ShadingMode (tracing.rs:29-32)");
   if (cam->path_samples != 1) return fail(RT_ERR_UNSUPPORTED, "path_samples must be 1 (tracing.rs:146,370)");
   if (cam->screen_width == 0 || cam->screen_height == 0) return fail(RT_ERR_INVALID, "empty image");
   if ((uint64_t)cam->screen_width * cam->screen_height > (1ull << 31)) return fail(RT_ERR_INVALID, "image too large");
@@ -213,6 +213,14 @@ void fill_frame_camera(const rt_camera& cam, uint64_t seed, rt_frame& fr) {
   fr.focus_dist = cam.focus_dist;
   fr.lens_radius = cam.lens_radius;
   fr.t_min = 0.001f;  // tracing.rs:305
+  if (cam.shading_mode == RT_SHADE_PHONG) {
+    fr.phong = 1;
+    fr.t_min = 0.0f;  // tracing.rs:279,290
+  }
+  if (cam.projection_mode == RT_PROJ_ORTHOGRAPHIC) {
+    fr.ortho = 1;
+    for (int k = 0; k < 3; ++k) fr.view_dir[k] = cam.view_dir[k];
+  }
   fr.t_max = cam.max_trace_dist;
   fr.spp = cam.aa_sample_count;
   fr.width = cam.screen_width;
@@ -309,6 +317,10 @@ int run_wavefront(rt_scene* s, const rt_frame& fr_in, unsigned long long total, 
   nlanes = std::max(1, std::min(nlanes, RT_MAX_LANES));
   if (total < (unsigned long long)nlanes * 65536ull) nlanes = 1;  // tiny jobs: one lane
   rt_frame fr = fr_in;
+  if (fr.phong) {  // camera ray + shadow ray pairs: slot i of the shadow pass belongs to slot i of the camera pass
+    nlanes = 1;
+    fr.sort_enabled = 0;
+  }
   fr.capacity = std::max<uint32_t>(128u, (fr.capacity / (uint32_t)nlanes + 127u) / 128u * 128u);
   for (int li = 0; li < nlanes; ++li)
     if ((rc = ensure_lane(s, li, fr.capacity)) != RT_OK) return rc;
@@ -367,6 +379,22 @@ int run_wavefront(rt_scene* s, const rt_frame& fr_in, unsigned long long total, 
         }
         rt::launch_trace(s->dev, fr, L.ctrl, L.paths[cur], L.hits, L.sort, count, s->persistent_blocks, st);  // dominant kernel
         if (timed) CUDA_TRY(cudaEventRecord(e1, st));
+        if (fr.phong) {
+          // ShadingMode::Phong (tracing.rs:277-297).  k_phong_primary leaves n_next = n_rays, so the second
+          // k_advance admits no new work (a batch is either full or the last one) and the shadow rays keep their slots.
+          rt::launch_phong_primary(s->dev, fr, L.ctrl, L.paths[cur], L.paths[nxt], L.hits, st);
+          rt::launch_advance(L.ctrl, fr.capacity, st);
+          rt_frame fs = fr;
+          fs.ray_tmax_from_c = 1;
+          rt::launch_trace(s->dev, fs, L.ctrl, L.paths[nxt], L.hits, L.sort, count, s->persistent_blocks, st);
+          rt::launch_phong_shadow(s->dev, fr, L.ctrl, L.paths[nxt], L.hits, d_accum, st);
+          if (timed) {
+            CUDA_TRY(cudaEventRecord(e2, st));
+            ++R.timed_iters;
+          }
+          R.launches += 7; R.ext += 2; R.shd += 2; R.it += 2;
+          continue;
+        }
         rt::launch_sort(s->dev, fr, L.ctrl, L.hits, L.queues, st);
         rt::launch_shade(s->dev, fr, L.ctrl, L.paths[cur], L.paths[nxt], L.hits, L.queues, d_accum, L.sort, count, st);
         rt::launch_raysort(fr, L.ctrl, L.sort, st);
@@ -420,7 +448,7 @@ int run_wavefront(rt_scene* s, const rt_frame& fr_in, unsigned long long total, 
       const LaneRun& R = run[li];
       const rt_ctrl& c = *L.h_ctrl;
       stats->samples += c.n_samples - c.counters[7];
-      stats->rays += c.n_rays_total - c.counters[7];
+      stats->rays += c.n_rays_total - c.counters[7] - c.counters[11];  // [11]: Phong shadow slots of missed camera rays
       stats->iterations += c.iterations;
       stats->kernel_launches += R.launches;
       // report the launches that did work, not the no-op tail queued behind the `done` poll
@@ -729,6 +757,10 @@ int rt_render_accum(rt_scene* s, const rt_camera* cam, const rt_render_opts* opt
   if (opts) o = *opts;
   rt_frame fr;
   fill_frame_camera(*cam, o.seed, fr);
+  for (int k = 0; k < 3; ++k) {
+    fr.light[k] = o.point_light_pos[k];
+    fr.ambient[k] = o.ambient[k];
+  }
   unsigned long long total = 0;
   if ((rc = plan_shard(*cam, o, fr, total)) != RT_OK) return rc;
   fr.capacity = pick_capacity(total, o.wavefront);

@@ -149,6 +149,12 @@ __device__ __forceinline__ void camera_ray(const rt_frame& fr, uint32_t x, uint3
      c2 = mk(fr.rot2[0], fr.rot2[1], fr.rot2[2]);
   f3 rl = c0 * lens.x + c1 * lens.y + c2 * lens.z;
   origin = mk(fr.eye[0], fr.eye[1], fr.eye[2]) + rl;
+  if (fr.ortho) {
+    // CameraProjectionMode::Orthographic, tracing.rs:196,200 as written: the camera-space pixel centre is used as a
+    // WORLD position (eyepoint ignored) and view_dir is rotated once more by `rotation`
+    origin = mk(center.x, center.y, 0.0f);
+    dcam = mk(fr.view_dir[0], fr.view_dir[1], fr.view_dir[2]);
+  }
   direction = c0 * dcam.x + c1 * dcam.y + c2 * dcam.z;
 }
 
@@ -270,6 +276,7 @@ struct Trav {
   uint32_t slot;
   f3 o, d, inv, oi; // current-space ray (world or instance), reciprocal direction, -o*inv
   float t_min, t_max;
+  float ray_t_max;  // the ray's own upper limit (t_max is temporarily replaced during a volume boundary query)
   uint32_t entry;   // packed node link being visited, RT_ENTRY_NONE when a pop is needed
   int sp;
   int cur_obj;
@@ -946,6 +953,7 @@ __global__ void __launch_bounds__(RT_BLOCK, RT_EXTEND_MIN_BLOCKS) k_trace(rt_dev
           hits.obj[my] = -1;  // "no ray" marker written by k_raygen
         } else {
           T.slot = my;
+          T.t_max = T.ray_t_max = fr.ray_tmax_from_c ? RT_LDS(&cur.C[my]).w : fr.t_max;  // Phong shadow rays end at the light
           trav_begin<COUNT>(sc, T, wo, wd);
           have = true;
           fin = false;
@@ -961,7 +969,7 @@ __global__ void __launch_bounds__(RT_BLOCK, RT_EXTEND_MIN_BLOCKS) k_trace(rt_dev
     // ---- traverse until enough lanes are idle again (or nothing is left to fetch)
     const bool can_refill = !(exhausted && c_next >= c_end);
     for (;;) {
-      if (have && !fin) fin = trav_round<COUNT, VOLMESH>(sc, T, fr.t_min, fr.t_max);
+      if (have && !fin) fin = trav_round<COUNT, VOLMESH>(sc, T, fr.t_min, T.ray_t_max);
       uint32_t run = __ballot_sync(FULL, have && !fin);
       if (run == 0) break;
       if (can_refill && 32 - __popc(run) >= RT_REFILL_MIN) break;
@@ -1397,6 +1405,104 @@ __global__ void __launch_bounds__(256) k_raysort_scatter(rt_ctrl* __restrict__ c
   sort.order[s_slice[key >> 10] + base + __popc(peers & ((1u << lane) - 1u))] = i;
 }
 
+// ------------------------------------------------------------------ k_phong_primary / k_phong_shadow
+// ShadingMode::Phong (Scene::phong_shade_ray, tracing.rs:277-297), the reference's debug shading: one camera ray,
+// one shadow ray towards point_light_pos, no recursion.  Both queries use t_min = 0.
+//   k_phong_primary: hit frame, ambient + diffuse * brdf + specular * 0.4 (parked in the T slot of the shadow ray),
+//                    shadow ray from hitpoint + 0.01 n towards the light, limited to the distance to the light (C.w)
+//   k_phong_shadow : shadow weight (tracing.rs:290-293: 0.3 unless the occluder lies in the far half of the segment)
+//                    and accumulation
+__global__ void __launch_bounds__(RT_BLOCK) k_phong_primary(rt_dev_scene sc, rt_frame fr, rt_ctrl* __restrict__ ctrl,
+                                                            rt_paths cur, rt_paths nxt, rt_hits hits) {
+  const uint32_t n_rays = ctrl->n_rays;
+  const uint32_t i = blockIdx.x * RT_BLOCK + threadIdx.x;
+  if (i == 0) ctrl->n_next = n_rays;  // no compaction: shadow ray i belongs to camera ray i
+  if (i >= n_rays) return;
+  int obj = hits.obj[i];
+  {
+    uint32_t miss = __ballot_sync(__activemask(), obj < 0);
+    if (miss && (threadIdx.x & 31u) == (uint32_t)(__ffs(__activemask()) - 1)) atomicAdd(&ctrl->counters[11], (unsigned long long)__popc(miss));
+  }
+  if (obj < 0) {  // background_color: black; also the "no ray" marker for k_trace
+    nxt.A[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    nxt.B[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    nxt.C[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    return;
+  }
+  float4 a = cur.A[i], bq = cur.B[i], c = cur.C[i];
+  f3 o = mk(a.x, a.y, a.z), d = mk(a.w, bq.x, bq.y);
+  uint32_t pixel = fbits(c.y), sb = fbits(c.z);
+  float4 hr = hits.H[i];
+  Best best;
+  best.t = hr.x; best.u = hr.y; best.v = hr.z; best.prim = fbits(hr.w);
+  best.obj = obj;
+  Surface sf;
+  resolve_hit<false>(sc, o, d, best, sf, ctrl->counters);
+  const uint32_t cls = sf.meta & 7u, id = sf.meta >> 4;
+  f3 albedo;
+  float roughness, metallic;
+  if (cls == RT_CLASS_PARAM_TEX) {
+    uint32_t q = id * RT_OBJ_QUADS;
+    float4 m7 = ldq(sc.objects, q + 7), m8 = ldq(sc.objects, q + 8);
+    int ta = (int)fbits(m7.z), tm = (int)fbits(m8.x), tr = (int)fbits(m8.y);
+    albedo = ta >= 0 ? tex_sample(sc, ta, sf.u, sf.v) : mk(0.f, 0.f, 0.f);
+    metallic = tm >= 0 ? tex_sample(sc, tm, sf.u, sf.v).x : 0.0f;
+    roughness = tr >= 0 ? tex_sample(sc, tr, sf.u, sf.v).x : 1.0f;
+  } else {
+    float4 m0 = ldq(sc.mats, id * RT_MAT_QUADS), m1 = ldq(sc.mats, id * RT_MAT_QUADS + 1);
+    albedo = mk(m0.x, m0.y, m0.z);
+    roughness = m0.w;
+    metallic = m1.w;
+  }
+  // hit.material.scatter(&hit, ray).1 : the attenuation term of each material (materials.rs:33-166)
+  f3 brdf;
+  if (cls == RT_CLASS_LAMBERT) brdf = albedo / RT_PI;
+  else if (cls == RT_CLASS_DIELECTRIC) brdf = mk(1.0f, 1.0f, 1.0f);
+  else if (cls == RT_CLASS_METAL || cls == RT_CLASS_ISOTROPIC) brdf = albedo;
+  else {
+    u4 r = philox4x32_10(pixel, sb & 0xFFFFFFu, 0u, 0u, fr.k0, fr.k1);
+    float fres = fresnelf(d, sf.n, 1.5f);
+    float k_s = fres * (1.0f - roughness);
+    float k_d = (1.0f - k_s) * (1.0f - metallic);
+    brdf = u01(r.x) < k_d ? albedo / RT_PI : (1.0f - metallic) * mk(1.0f, 1.0f, 1.0f) + metallic * albedo;
+  }
+  const f3 light = mk(fr.light[0], fr.light[1], fr.light[2]), eye = mk(fr.eye[0], fr.eye[1], fr.eye[2]);
+  const f3 n = sf.n, hp = sf.hp;
+  f3 to_light = normalize(light - hp);
+  f3 to_camera = normalize(eye - hp);
+  f3 reflected = -to_light + 2.0f * dot(to_light, n) * n;
+  float diffuse_weight = clampf(dot(n, to_light), 0.0f, 1.0f);
+  float specular_weight = powf(clampf(dot(to_camera, reflected), 0.0f, 1.0f), 40.0f);
+  f3 partial = mk(fr.ambient[0], fr.ambient[1], fr.ambient[2]) + diffuse_weight * brdf + specular_weight * mk(0.4f, 0.4f, 0.4f);
+  f3 so = hp + 0.01f * n;
+  float dist = sqrtf(mag2(light - hp));
+  nxt.A[i] = make_float4(so.x, so.y, so.z, to_light.x);
+  nxt.B[i] = make_float4(to_light.y, to_light.z, partial.x, partial.y);
+  nxt.C[i] = make_float4(partial.z, __uint_as_float(pixel), __uint_as_float((sb & 0xFFFFFFu) | (1u << 24)), dist);
+}
+__global__ void __launch_bounds__(RT_BLOCK) k_phong_shadow(rt_dev_scene sc, rt_frame fr, rt_ctrl* __restrict__ ctrl, rt_paths cur,
+                                                           rt_hits hits, long long* __restrict__ accum) {
+  const uint32_t i = blockIdx.x * RT_BLOCK + threadIdx.x;
+  if (i >= ctrl->n_rays) return;
+  float4 a = cur.A[i], bq = cur.B[i], c = cur.C[i];
+  f3 o = mk(a.x, a.y, a.z), d = mk(a.w, bq.x, bq.y);
+  if (d.x == 0.0f && d.y == 0.0f && d.z == 0.0f && bq.z == 0.0f) return;  // the camera ray missed: black
+  f3 partial = mk(bq.z, bq.w, c.x);
+  float weight = 1.0f;
+  int obj = hits.obj[i];
+  if (obj >= 0) {
+    float4 hr = hits.H[i];
+    Best best;
+    best.t = hr.x; best.u = hr.y; best.v = hr.z; best.prim = fbits(hr.w);
+    best.obj = obj;
+    Surface sf;
+    resolve_hit<false>(sc, o, d, best, sf, ctrl->counters);
+    const f3 light = mk(fr.light[0], fr.light[1], fr.light[2]);
+    weight = best.t * best.t > mag2(light - sf.hp) ? 1.0f : 0.3f;
+  }
+  accum_add(accum, fbits(c.y), weight * partial);
+}
+
 // ------------------------------------------------------------------ k_resolve (Q12)
 __global__ void k_resolve(const long long* __restrict__ accum, uint32_t npix, uint32_t spp, float gamma,
                           float* __restrict__ out_linear, uint8_t* __restrict__ out_rgb8) {
@@ -1495,6 +1601,14 @@ void launch_shade(const rt_dev_scene& sc, const rt_frame& fr, rt_ctrl* ctrl, rt_
   uint32_t grid = (fr.capacity + RT_BLOCK - 1) / RT_BLOCK + RT_NUM_CLASSES;
   if (count) k_shade<true><<<grid, RT_BLOCK, 0, st>>>(sc, fr, ctrl, cur, nxt, hits, queues, accum, sort);
   else k_shade<false><<<grid, RT_BLOCK, 0, st>>>(sc, fr, ctrl, cur, nxt, hits, queues, accum, sort);
+}
+void launch_phong_primary(const rt_dev_scene& sc, const rt_frame& fr, rt_ctrl* ctrl, rt_paths cur, rt_paths nxt, rt_hits hits,
+                          cudaStream_t st) {
+  k_phong_primary<<<(fr.capacity + RT_BLOCK - 1) / RT_BLOCK, RT_BLOCK, 0, st>>>(sc, fr, ctrl, cur, nxt, hits);
+}
+void launch_phong_shadow(const rt_dev_scene& sc, const rt_frame& fr, rt_ctrl* ctrl, rt_paths cur, rt_hits hits, long long* accum,
+                         cudaStream_t st) {
+  k_phong_shadow<<<(fr.capacity + RT_BLOCK - 1) / RT_BLOCK, RT_BLOCK, 0, st>>>(sc, fr, ctrl, cur, hits, accum);
 }
 void launch_resolve(const long long* accum, uint32_t npix, uint32_t spp, float gamma, float* out_linear,
                     uint8_t* out_rgb8, cudaStream_t st) {

@@ -48,6 +48,10 @@ void launch_surface(const rt_dev_scene& sc, const rt_frame& fr, rt_ctrl* ctrl, r
 int trace_blocks_per_sm();
 void launch_shade(const rt_dev_scene& sc, const rt_frame& fr, rt_ctrl* ctrl, rt_paths cur, rt_paths nxt, rt_hits hits,
                   const uint32_t* queues, long long* accum, rt_sortbuf sort, bool count, cudaStream_t st);
+void launch_phong_primary(const rt_dev_scene& sc, const rt_frame& fr, rt_ctrl* ctrl, rt_paths cur, rt_paths nxt, rt_hits hits,
+                          cudaStream_t st);
+void launch_phong_shadow(const rt_dev_scene& sc, const rt_frame& fr, rt_ctrl* ctrl, rt_paths cur, rt_hits hits, long long* accum,
+                         cudaStream_t st);
 void launch_resolve(const long long* accum, uint32_t npix, uint32_t spp, float gamma, float* out_linear,
                     uint8_t* out_rgb8, cudaStream_t st);
 

@@ -105,6 +105,10 @@ struct rt_frame {
   uint32_t sample_major;            // 1: consecutive work indices walk the pixels (sample index changes slowest)
   unsigned long long pixel_slots;   // pixel slots of this shard (work items = pixel_slots * sample_count)
   uint32_t capacity;                // wavefront width P
+  // debug modes of the reference: orthographic projection (tracing.rs:196,200), Phong shading (tracing.rs:277-297)
+  uint32_t phong;                   // host-side switch: camera ray + shadow ray pairs instead of path iterations
+  uint32_t ortho, ray_tmax_from_c;  // ray_tmax_from_c: a ray's own t_max travels in C.w (Phong shadow rays)
+  float view_dir[3], light[3], ambient[3];
   // secondary-ray sorting (k_shade -> k_raysort_*): origin cell (16^3 over the TLAS box, Morton order) | direction octant
   uint32_t sort_enabled;
   float sort_min[3], sort_scale[3];

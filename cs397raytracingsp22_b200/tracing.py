@@ -92,8 +92,8 @@ class LowerContext:
 class Scene:  # tracing.rs:213-218
     camera: Camera
     objects: list
-    point_light_pos: tuple = (0.0, 1.0, 5.0)   # Phong only (debug mode, not on the GPU path)
-    ambient: tuple = (0.1, 0.1, 0.1)           # Phong only
+    point_light_pos: tuple = (0.0, 1.0, 5.0)   # ShadingMode::Phong only (tracing.rs:216)
+    ambient: tuple = (0.1, 0.1, 0.1)           # ShadingMode::Phong only (tracing.rs:217)
     seed: int = 0x5EED
     _backend: object = field(default=None, repr=False, compare=False)
 
@@ -118,6 +118,8 @@ class Scene:  # tracing.rs:213-218
         o = opts if opts is not None else _ffi.rt_render_opts()
         if opts is None:
             o.seed = self.seed
+        o.point_light_pos[:] = [float(v) for v in self.point_light_pos]
+        o.ambient[:] = [float(v) for v in self.ambient]
         return b.render(self.camera.to_c(), o, want_linear=want_linear, want_rgb8=want_rgb8)
 
     def render_to_image(self, device: int = 0) -> np.ndarray:

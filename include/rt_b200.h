@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define RT_B200_ABI_VERSION 1
+#define RT_B200_ABI_VERSION 2
 
 typedef enum rt_status {
   RT_OK = 0,
@@ -70,8 +70,8 @@ typedef struct rt_camera {
   float eyepoint[3];
   float view_dir[3];
   float up[3];
-  uint32_t projection_mode; /* only RT_PROJ_PERSPECTIVE is on the hot path */
-  uint32_t shading_mode;    /* only RT_SHADE_PATHTRACE is on the hot path  */
+  uint32_t projection_mode; /* RT_PROJ_ORTHOGRAPHIC is the reference's debug projection (tracing.rs:196,200) */
+  uint32_t shading_mode;    /* RT_SHADE_PHONG is the reference's debug shading (tracing.rs:277-297)          */
   uint32_t path_depth;
   uint32_t path_samples; /* must be 1 (tracing.rs:146,370) */
   uint32_t screen_width;
@@ -104,6 +104,8 @@ typedef struct rt_render_opts {
   uint32_t sample_end;    /*   both 0 => [0, aa_sample_count)                        */
   uint32_t wavefront;     /* paths in flight (0 => library default)                  */
   uint32_t flags;         /* RT_OPT_*                                                */
+  float point_light_pos[3]; /* Scene::point_light_pos, used by ShadingMode::Phong only (tracing.rs:216) */
+  float ambient[3];         /* Scene::ambient, Phong only (tracing.rs:217)                              */
 } rt_render_opts;
 
 typedef struct rt_stats {

@@ -304,7 +304,7 @@ struct RgbImage {  // image::RgbImage: row 0 = top
 struct Scene {  // tracing.rs:213-218
   Camera camera;
   std::vector<std::shared_ptr<const Intersectable>> objects;
-  Vec3 point_light_pos{0, 1, 5}, ambient{0.1f, 0.1f, 0.1f};  // Phong only (not on the GPU path)
+  Vec3 point_light_pos{0, 1, 5}, ambient{0.1f, 0.1f, 0.1f};  // ShadingMode::Phong only
   uint64_t seed = 0x5EED;
   // Scene::render_to_image, tracing.rs:221-263: lower -> commit -> render on CUDA device `device`
   RgbImage render_to_image(int device = 0, rt_stats* stats = nullptr) const {
@@ -321,6 +321,8 @@ struct Scene {  // tracing.rs:213-218
     rt_render_opts opts;
     std::memset(&opts, 0, sizeof opts);
     opts.seed = seed;
+    opts.point_light_pos[0] = point_light_pos.x; opts.point_light_pos[1] = point_light_pos.y; opts.point_light_pos[2] = point_light_pos.z;
+    opts.ambient[0] = ambient.x; opts.ambient[1] = ambient.y; opts.ambient[2] = ambient.z;
     RgbImage img;
     img.width = camera.screen_width;
     img.height = camera.screen_height;

@@ -385,6 +385,7 @@ struct orc_scene {
   std::vector<std::vector<uint8_t>> reach;  // brute mode: reachability masks per mesh
   std::vector<Object> objects;
   int n_volumes = 0;
+  float point_light_pos[3] = {0.0f, 1.0f, 5.0f}, ambient[3] = {0.1f, 0.1f, 0.1f};  // tracing.rs:216-217 (Phong only)
 };
 
 namespace {
@@ -748,7 +749,31 @@ V3 shade_ray(const RenderCtx& c, const Ray& ray, uint32_t depth, const RngKey& k
   return emission + integral;
 }
 
-// Camera::generate_rays for one sample index, tracing.rs:159-209 (perspective)
+// Scene::phong_shade_ray, tracing.rs:277-297 (ShadingMode::Phong, the reference's debug shading).  The scatter call of
+// line 294 draws from (pixel, sample, bounce 0); the shadow query counts as bounce 1 for the volume draws.
+V3 phong_shade_ray(const RenderCtx& c, const Ray& ray, const RngKey& key, Counters* cnt) {
+  Hit hit;
+  if (!scene_hit(*c.sc, ray, 0.0f, c.cam.max_trace_dist, c.mode, key, 0, hit, cnt)) return v3(0, 0, 0);
+  const V3 light = v3(c.sc->point_light_pos[0], c.sc->point_light_pos[1], c.sc->point_light_pos[2]);
+  const V3 ambient = v3(c.sc->ambient[0], c.sc->ambient[1], c.sc->ambient[2]);
+  const V3 eye = v3(c.cam.eyepoint[0], c.cam.eyepoint[1], c.cam.eyepoint[2]);
+  V3 to_light = normalize(light - hit.hitpoint);
+  V3 to_camera = normalize(eye - hit.hitpoint);
+  V3 reflected = -to_light + (2.0f * dot(to_light, hit.normal)) * hit.normal;
+  float diffuse_weight = rclamp(dot(hit.normal, to_light), 0.0f, 1.0f);
+  float specular_weight = std::pow(rclamp(dot(to_camera, reflected), 0.0f, 1.0f), 40.0f);
+  Ray shadow_ray;
+  shadow_ray.origin = hit.hitpoint + 0.01f * hit.normal;
+  shadow_ray.direction = to_light;
+  Hit sh;
+  float shadow_weight = 1.0f;
+  if (scene_hit(*c.sc, shadow_ray, 0.0f, std::sqrt(mag2(light - hit.hitpoint)), c.mode, key, 1, sh, cnt))
+    shadow_weight = sh.distance * sh.distance > mag2(light - sh.hitpoint) ? 1.0f : 0.3f;
+  const rt_material_desc& m = hit.material >= 0 ? c.sc->materials[hit.material].d : hit.param;
+  Scatter sc = scatter(m, hit, ray, draw(key, 0, 0));
+  return shadow_weight * (ambient + diffuse_weight * sc.brdf + specular_weight * v3(0.4f, 0.4f, 0.4f));
+}
+// Camera::generate_rays for one sample index, tracing.rs:159-209
 inline Ray camera_ray(const rt_camera& cam, uint32_t sx, uint32_t sy, uint32_t i, const RngKey& key,
                       float* offset_out) {
   float pixel_size = 1.0f / (float)cam.screen_height;
@@ -778,6 +803,12 @@ inline Ray camera_ray(const rt_camera& cam, uint32_t sx, uint32_t sy, uint32_t i
   Ray ray;
   ray.origin = v3(cam.eyepoint[0], cam.eyepoint[1], cam.eyepoint[2]) + rot(lens_origin);
   ray.direction = rot(normalize(focus - lens_origin));
+  if (cam.projection_mode == RT_PROJ_ORTHOGRAPHIC) {
+    // tracing.rs:196,200 as written: the camera-space pixel centre is the WORLD origin of the ray (the eyepoint is
+    // not used) and view_dir goes through `rotation` like a camera-space direction
+    ray.origin = v3(center.x, center.y, 0.0f);
+    ray.direction = rot(view);
+  }
   return ray;
 }
 
@@ -800,7 +831,7 @@ inline void output_transform(V3 mean, float gamma, uint8_t* rgb) {
 
 inline int check_camera(const rt_camera* cam) {
   if (!cam) return RT_ERR_INVALID;
-  if (cam->projection_mode != RT_PROJ_PERSPECTIVE || cam->shading_mode != RT_SHADE_PATHTRACE) return RT_ERR_UNSUPPORTED;
+  if (cam->projection_mode > RT_PROJ_PERSPECTIVE || cam->shading_mode > RT_SHADE_PATHTRACE) return RT_ERR_INVALID;
   if (cam->path_samples != 1) return RT_ERR_UNSUPPORTED;
   if (cam->screen_width == 0 || cam->screen_height == 0 || cam->aa_sample_count == 0) return RT_ERR_INVALID;
   return RT_OK;
@@ -941,6 +972,16 @@ int orc_add_volume_mesh(orc_scene* s, int mesh, const float xform[16], const flo
   return (int)s->objects.size() - 1;
 }
 
+// Scene::point_light_pos / Scene::ambient (tracing.rs:216-217), used by ShadingMode::Phong only
+int orc_set_lights(orc_scene* s, const float point_light_pos[3], const float ambient[3]) {
+  if (!s || !point_light_pos || !ambient) return RT_ERR_INVALID;
+  for (int k = 0; k < 3; ++k) {
+    s->point_light_pos[k] = point_light_pos[k];
+    s->ambient[k] = ambient[k];
+  }
+  return RT_OK;
+}
+
 // Scene::render_to_image, tracing.rs:221-263.  mode: 0 = reference tree, 1 = brute force.
 // Samples [sample_begin, sample_end) of every pixel; the mean divides by their count.
 int orc_render(const orc_scene* s, const rt_camera* cam, uint64_t seed, int mode, uint32_t sample_begin,
@@ -964,7 +1005,8 @@ int orc_render(const orc_scene* s, const rt_camera* cam, uint64_t seed, int mode
       for (uint32_t i = sample_begin; i < sample_end; ++i) {
         RngKey key{c.k0, c.k1, pixel, i};
         Ray ray = camera_ray(*cam, x, (uint32_t)y, i, key, nullptr);
-        final_color = final_color + shade_ray(c, ray, 0, key, &cnt);
+        final_color = final_color + (cam->shading_mode == RT_SHADE_PHONG ? phong_shade_ray(c, ray, key, &cnt)
+                                                                         : shade_ray(c, ray, 0, key, &cnt));
       }
       final_color = final_color / (float)(sample_end - sample_begin);
       if (out_linear_rgb) {

@@ -61,6 +61,7 @@ def load():
         "orc_add_volume_sphere": (C.c_int, [_P, _F, C.c_float, C.c_float, C.c_int]),
         "orc_add_volume_mesh": (C.c_int, [_P, C.c_int, _F, _F, C.c_float, C.c_int]),
         "orc_render": (C.c_int, [_P, cam, C.c_uint64, C.c_int, C.c_uint32, C.c_uint32, C.c_int, _F, _U8, st]),
+        "orc_set_lights": (C.c_int, [_P, _F, _F]),
         "orc_trace_primary": (C.c_int, [_P, cam, C.c_uint64, C.c_int, C.c_uint32, _I, _I, _F, _F, _F]),
         "orc_intersect_rays": (C.c_int, [_P, C.c_uint64, C.c_int, C.c_uint32, _F, C.c_float, C.c_float, _I, _I, _F,
                                          _F, _F, _F, _I]),
@@ -154,6 +155,11 @@ class OracleBackend:
     def commit(self, device: int = 0):
         pass
 
+    def set_lights(self, point_light_pos, ambient):
+        """Scene::point_light_pos / Scene::ambient (tracing.rs:216-217), ShadingMode::Phong only."""
+        p = np.asarray(point_light_pos, np.float32); a = np.asarray(ambient, np.float32)
+        _check(self.lib.orc_set_lights(self.handle, _ffi.fptr(p), _ffi.fptr(a)))
+
     def render(self, cam, seed=0x5EED, mode=MODE_REF_TREE, sample_begin=0, sample_end=0, nthreads=0,
                want_linear=True, want_rgb8=True):
         w, h = cam.screen_width, cam.screen_height
@@ -188,6 +194,7 @@ class OracleBackend:
 def lower_to_oracle(scene) -> OracleBackend:
     b = OracleBackend()
     scene.lower(b)
+    b.set_lights(scene.point_light_pos, scene.ambient)
     return b
 
 

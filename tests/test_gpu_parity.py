@@ -138,10 +138,10 @@ def test_empty_and_degenerate_inputs(gpu):
     g2, o2 = _both(sc2)
     a, b = g2.trace_primary(cam.to_c(), 1, 0), o2.trace_primary(cam.to_c(), 1, 0)
     assert np.array_equal(a["obj"], b["obj"]) and not (a["obj"] == 0).any() and (a["obj"] == 1).any()
-    # unsupported modes are refused, not approximated
-    ortho = rt.Camera(projection_mode=rt.CameraProjectionMode.Orthographic)
+    # unsupported settings are refused, not approximated
+    two = rt.Camera(path_samples=2)
     with pytest.raises(_ffi.RtError) as e:
-        g.render(ortho.to_c())
+        g.render(two.to_c())
     assert e.value.code == _ffi.RT_ERR_UNSUPPORTED
 
 
@@ -150,6 +150,8 @@ def _render_pair(sc, spp_kw=None):
     cam = sc.camera.to_c()
     opts = _ffi.rt_render_opts()
     opts.seed = SEED
+    opts.point_light_pos[:] = sc.point_light_pos
+    opts.ambient[:] = sc.ambient
     lin_g, rgb_g, st_g = g.render(cam, opts)
     lin_o, rgb_o, st_o = o.render(cam, seed=SEED, mode=O.MODE_REF_TREE)
     return lin_g, rgb_g, st_g, lin_o, rgb_o, st_o
@@ -194,6 +196,77 @@ def test_converged_images_rmse(gpu, small_scenes, name, kw):
     assert psnr > 50.0
     d8 = np.abs(rgb_g.astype(np.int32) - rgb_o.astype(np.int32)).max(axis=2)
     assert (d8 <= 1).mean() > 0.99
+
+
+def _debug_mode_scene(width=128, height=72, spp=4):
+    """Objects inside the window the orthographic camera of tracing.rs:196 sees: x in +-aspect/2, y in +-0.5, looking
+    down -z from the plane z = 0 whatever the eyepoint is."""
+    from cs397raytracingsp22_b200 import scenes
+    cam = rt.Camera(eyepoint=(0.0, 0.0, 2.0), focal_length=2.2, screen_width=width, screen_height=height, aa_sample_count=spp,
+                    max_trace_dist=100.0, path_depth=4)
+    sc = rt.Scene(camera=cam, objects=[], point_light_pos=(0.6, 0.9, 1.0), ambient=(0.05, 0.06, 0.07))
+    wall = rt.Lambertian(albedo=(0.7, 0.7, 0.6))
+    sc.objects.append(rt.Plane(point=(0, -0.48, 0), normal=(0, 1.0, 0), material=rt.Lambertian(albedo=(0.5, 0.5, 0.7))))
+    sc.objects.append(rt.Triangle(a=(-0.7, -2.0, -4.0), b=(3.0, -2.0, -4.0), c=(3.0, 2.0, -4.0), material=wall))
+    sc.objects.append(rt.Triangle(a=(-0.7, -2.0, -4.0), b=(3.0, 2.0, -4.0), c=(-0.7, 2.0, -4.0), material=wall))
+    sc.objects.append(rt.Sphere(center=(-0.45, 0.1, -2.0), radius=0.3, material=rt.Metal(albedo=(0.9, 0.6, 0.3), roughness=0.1)))
+    sc.objects.append(rt.Sphere(center=(0.5, -0.15, -1.5), radius=0.25, material=rt.Dielectric(idx_of_refraction=1.5)))
+    sc.objects.append(rt.Sphere(center=(0.1, 0.3, -1.0), radius=0.12,
+                                material=rt.ParameterizedMaterial(albedo=(0.2, 0.5, 0.9), roughness=0.4, metallic=0.5)))
+    sc.objects.append(rt.Triangle(a=(-0.8, -0.45, -3.0), b=(0.8, -0.45, -3.0), c=(0.0, 0.45, -3.5),
+                                  material=rt.Lambertian(albedo=(0.3, 0.8, 0.3))))
+    sc.objects.append(rt.ConvexVolume(boundary=rt.Sphere(center=(-0.1, -0.2, -0.8), radius=0.2, material=None),
+                                      phase_function=rt.Isotropic(albedo=(0.8, 0.8, 0.9)), density=3.0))
+    cg = rt.cgmath
+    xf = cg.chain(cg.from_translation((0.45, 0.2, -2.5)), cg.from_angle_x(-90.0), cg.from_scale(0.12))
+    sc.objects.append(rt.StaticMesh.load_from_file(scenes.obj_path("teapot"), material=rt.Lambertian(albedo=(0.8, 0.3, 0.3)),
+                                                   transform=xf))
+    return sc
+
+
+@pytest.mark.parametrize("projection", ["Perspective", "Orthographic"])
+def test_phong_debug_shading_matches_the_oracle(gpu, projection):
+    """ShadingMode::Phong (tracing.rs:277-297) in both projections: one camera ray + one shadow ray per sample, no
+    Monte-Carlo integration, so the images agree to float rounding except where an ulp flips a discrete decision (a
+    silhouette, the 0.3/1.0 shadow weight, the diffuse/specular choice of the parameterised material)."""
+    sc = _debug_mode_scene()
+    sc.camera.shading_mode = rt.ShadingMode.Phong
+    sc.camera.projection_mode = getattr(rt.CameraProjectionMode, projection)
+    lin_g, rgb_g, st_g, lin_o, rgb_o, st_o = _render_pair(sc)
+    assert st_g.samples == st_o.samples == 128 * 72 * 4
+    assert st_g.rays == st_o.rays                      # camera rays + one shadow ray per camera hit
+    assert lin_o.max() > 0.2 and (lin_o.max(axis=2) == 0).mean() < 0.9
+    diff = np.abs(lin_g - lin_o).max(axis=2)
+    assert np.median(diff) <= 1e-6
+    assert (diff > 1e-4).mean() < 0.005, f"{(diff > 1e-4).mean():.4f} of pixels differ"
+    d8 = np.abs(rgb_g.astype(np.int32) - rgb_o.astype(np.int32)).max(axis=2)
+    assert (d8 <= 1).mean() > 0.995
+    shard = D.shard_opts(0, 1, SEED, mode="tiles", tile=16)
+    shard.point_light_pos[:] = sc.point_light_pos
+    shard.ambient[:] = sc.ambient
+    lin_t = sc.commit(0).render(sc.camera.to_c(), shard)[0]
+    assert np.array_equal(lin_t, lin_g)                # work order does not matter in this mode either
+
+
+def test_orthographic_path_tracing_and_primary_hits(gpu):
+    """CameraProjectionMode::Orthographic (tracing.rs:196,200) under the path tracer: primary ids bit-exact, low-spp
+    image tracks the oracle sample for sample."""
+    sc = _debug_mode_scene(spp=16)
+    sc.objects.append(rt.Sphere(center=(0.0, 3.0, 1.0), radius=1.5, material=rt.Lambertian(albedo=(0, 0, 0), emission=(6, 6, 6))))
+    sc.camera.projection_mode = rt.CameraProjectionMode.Orthographic
+    g, o = _both(sc)
+    cam = sc.camera.to_c()
+    for sample in (0, 7):
+        hg = g.trace_primary(cam, SEED, sample)
+        ho = o.trace_primary(cam, SEED, sample)
+        assert np.array_equal(hg["ray"], ho["ray"])
+        assert (ho["ray"][:, 2] == 0).all()            # every ray starts on the plane z = 0
+        _assert_hits_match(hg, ho, f"ortho sample {sample}", vol_objs=_volume_ids(sc))
+    lin_g, rgb_g, st_g, lin_o, rgb_o, st_o = _render_pair(sc)
+    diff = np.abs(lin_g - lin_o)
+    scale = max(float(lin_o.mean()), 1e-6)
+    assert np.median(diff) <= 1e-5 * max(scale, 1.0)
+    assert (diff.max(axis=2) > 1e-3 * np.maximum(lin_o.max(axis=2), scale)).mean() < 0.03
 
 
 def test_furnace_on_the_gpu(gpu):
