@@ -112,6 +112,7 @@ SIGNATURES = {
     "rt_tga_decode": (C.c_int, [_U8, C.c_size_t, C.POINTER(_U8), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]),
     "rt_tga_encode_rgb8": (C.c_int, [_U8, C.c_uint32, C.c_uint32, C.POINTER(_U8), C.POINTER(C.c_size_t)]),
     "rt_png_decode": (C.c_int, [_U8, C.c_size_t, C.POINTER(_U8), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]),
+    "rt_jpeg_decode": (C.c_int, [_U8, C.c_size_t, C.POINTER(_U8), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]),
     "rt_png_encode_rgb8": (C.c_int, [_U8, C.c_uint32, C.c_uint32, C.POINTER(_U8), C.POINTER(C.c_size_t)]),
     "rt_free": (None, [_P]),
     "rt_mesh_reachability": (C.c_int, [_F, C.c_uint32, C.POINTER(C.c_uint32), C.c_uint32, _U8]),
@@ -201,6 +202,18 @@ def png_decode(data: bytes) -> np.ndarray:
     out = _U8()
     w, h = C.c_uint32(), C.c_uint32()
     check(lib.rt_png_decode(u8ptr(buf), len(data), C.byref(out), C.byref(w), C.byref(h)))
+    try:
+        return np.ctypeslib.as_array(out, shape=(h.value, w.value, 3)).copy()
+    finally:
+        lib.rt_free(out)
+
+
+def jpeg_decode(data: bytes) -> np.ndarray:
+    lib = load()
+    buf = np.frombuffer(data, dtype=np.uint8).copy()
+    out = _U8()
+    w, h = C.c_uint32(), C.c_uint32()
+    check(lib.rt_jpeg_decode(u8ptr(buf), len(data), C.byref(out), C.byref(w), C.byref(h)))
     try:
         return np.ctypeslib.as_array(out, shape=(h.value, w.value, 3)).copy()
     finally:

@@ -1024,6 +1024,12 @@ int rt_png_decode(const uint8_t* bytes, size_t len, uint8_t** rgb, uint32_t* w, 
   int rc = rt::png_decode(bytes, len, rgb, w, h, err);
   return rc == RT_OK ? RT_OK : fail(rc, err);
 }
+int rt_jpeg_decode(const uint8_t* bytes, size_t len, uint8_t** rgb, uint32_t* w, uint32_t* h) {
+  if (!bytes || !rgb || !w || !h) return fail(RT_ERR_INVALID, "rt_jpeg_decode: bad argument");
+  std::string err;
+  int rc = rt::jpeg_decode(bytes, len, rgb, w, h, err);
+  return rc == RT_OK ? RT_OK : fail(rc, err);
+}
 int rt_png_encode_rgb8(const uint8_t* rgb, uint32_t w, uint32_t h, uint8_t** bytes, size_t* len) {
   if (!bytes || !len) return fail(RT_ERR_INVALID, "rt_png_encode_rgb8: bad argument");
   int rc = rt::png_encode_rgb8(rgb, w, h, bytes, len);

@@ -86,6 +86,7 @@ int obj_parse(const char* text, size_t len, rt_obj_mesh* out, std::string& err);
 int tga_decode(const uint8_t* bytes, size_t len, uint8_t** rgb, uint32_t* w, uint32_t* h, std::string& err);
 int tga_encode_rgb8(const uint8_t* rgb, uint32_t w, uint32_t h, uint8_t** bytes, size_t* len);
 int png_decode(const uint8_t* bytes, size_t len, uint8_t** rgb, uint32_t* w, uint32_t* h, std::string& err);  // rt_png.cpp
+int jpeg_decode(const uint8_t* bytes, size_t len, uint8_t** rgb, uint32_t* w, uint32_t* h, std::string& err);  // rt_jpeg.cpp
 int png_encode_rgb8(const uint8_t* rgb, uint32_t w, uint32_t h, uint8_t** bytes, size_t* len);
 
 }  // namespace rt

@@ -147,8 +147,9 @@ def c3_materials(width=1024, height=1024, spp=1024, depth=10) -> Scene:
 
 
 def c4_drone(width=1920, height=1080, spp=1024, depth=10, map_size=2048) -> Scene:
-    """`run()` verbatim (tracing.rs:374-540); only resolution / spp differ and the drone maps are synthetic."""
-    maps = drone_maps(map_size)
+    """`run()` verbatim (tracing.rs:374-540); only resolution / spp differ and the drone maps are synthetic
+    (map_size=0: no maps at all, which is what the reference itself gets from its checkout)."""
+    maps = drone_maps(map_size) if map_size else [None] * 5
     drone = StaticMesh(load_obj(obj_path("drone")), maps, None,
                        cg.chain(cg.from_translation((0.0, 1.3, 1.7)), cg.from_angle_y(-60.0), cg.from_angle_x(180.0),
                                 cg.from_scale(0.0030)))

@@ -2,8 +2,8 @@
 
 `Texture.load_from_file` mirrors texture.rs:16-25: any decodable image -> RGB8, and **None on
 failure** (the reference silently renders with the Q7 defaults when a map is missing, as it does
-for the five Drone_*.tga maps absent from the checkout).  PNG and TGA are decoded by the library's own readers (csrc/rt_png.cpp, rt_lower.cpp); JPEG decoding (the `image`
-crate's job in the reference) is done with PIL.
+for the five Drone_*.tga maps absent from the checkout).  PNG, JPEG and TGA are decoded by the library's own
+readers (csrc/rt_png.cpp, rt_jpeg.cpp, rt_lower.cpp) - what the `image` crate does in the reference.
 """
 from __future__ import annotations
 
@@ -35,9 +35,10 @@ class Texture:
             if file_name.lower().endswith(".png"):
                 with open(file_name, "rb") as f:
                     return Texture(_ffi.png_decode(f.read()))
-            from PIL import Image
-            with Image.open(file_name) as im:
-                return Texture(np.asarray(im.convert("RGB"), dtype=np.uint8))
+            if file_name.lower().endswith((".jpg", ".jpeg")):
+                with open(file_name, "rb") as f:
+                    return Texture(_ffi.jpeg_decode(f.read()))
+            return None  # like image::open on a format it does not know: the caller gets no texture (texture.rs:17-22)
         except Exception:
             return None
 

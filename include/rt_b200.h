@@ -257,6 +257,9 @@ int rt_tga_encode_rgb8(const uint8_t* rgb, uint32_t w, uint32_t h, uint8_t** byt
  * Self-contained inflate, no zlib.  What image::open (texture.rs:17) and save_with_format (tracing.rs:546) do. */
 int rt_png_decode(const uint8_t* bytes, size_t len, uint8_t** rgb, uint32_t* w, uint32_t* h);
 int rt_png_encode_rgb8(const uint8_t* rgb, uint32_t w, uint32_t h, uint8_t** bytes, size_t* len);
+/* JPEG (baseline, extended sequential and progressive Huffman; 8 bit; grey or YCbCr/RGB; any sampling) -> RGB8
+ * top-down.  What image::open (texture.rs:17) does for the reference's .jpg textures through jpeg-decoder 0.1.22. */
+int rt_jpeg_decode(const uint8_t* bytes, size_t len, uint8_t** rgb, uint32_t* w, uint32_t* h);
 void rt_free(void* p);
 
 /* Reachability mask of the reference's index-order BVH (geometry.rs:190-217 with the

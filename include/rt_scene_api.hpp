@@ -120,7 +120,7 @@ struct Isotropic : Material {  // materials.rs:152-157
 };
 using MaterialRef = std::shared_ptr<const Material>;
 
-// ---- texture (texture.rs).  PNG and TGA are decoded natively (the library's readers); JPEG callers pass decoded RGB8.
+// ---- texture (texture.rs).  PNG, JPEG and TGA are decoded by the library's own readers (format by magic number).
 struct Texture {
   uint32_t width = 0, height = 0;
   std::vector<uint8_t> rgb8;
@@ -131,7 +131,10 @@ struct Texture {
     uint8_t* px = nullptr;
     uint32_t w = 0, h = 0;
     bool png = bytes.size() > 8 && bytes[0] == 137 && bytes[1] == 'P' && bytes[2] == 'N' && bytes[3] == 'G';
-    int rc = png ? rt_png_decode(bytes.data(), bytes.size(), &px, &w, &h) : rt_tga_decode(bytes.data(), bytes.size(), &px, &w, &h);
+    bool jpeg = bytes.size() > 3 && bytes[0] == 0xFF && bytes[1] == 0xD8;
+    int rc = png    ? rt_png_decode(bytes.data(), bytes.size(), &px, &w, &h)
+             : jpeg ? rt_jpeg_decode(bytes.data(), bytes.size(), &px, &w, &h)
+                    : rt_tga_decode(bytes.data(), bytes.size(), &px, &w, &h);
     if (rc != RT_OK) return std::nullopt;
     Texture t;
     t.width = w; t.height = h;
