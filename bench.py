@@ -388,7 +388,7 @@ def main():
                                                   "Philox key; one NCCL int64 reduce per frame" if world > 1 and args.shard == "weak"
                                                   else ("single GPU" if world == 1 else f"one frame sharded by {args.shard}")),
             "total_spp": total_spp, "l2": "flush (256 MiB memset between timed iterations)",
-            "wavefront": int(args.wavefront or (1 << 23)), "scene_build_s": build_s,
+            "wavefront": int(args.wavefront or (1 << 24)), "scene_build_s": build_s,
             "scene_bytes": int(g.device_bytes()),
         }),
         "rays_per_sec_M": rays_M, "rays_per_sample": job_rays / max(job_samples, 1),

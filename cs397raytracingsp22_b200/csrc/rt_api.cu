@@ -291,7 +291,7 @@ int plan_shard(const rt_camera& cam, const rt_render_opts& o, rt_frame& fr, unsi
 // paths in flight.  Every k_trace launch ends with a tail in which the last, longest ray batches finish on a nearly
 // empty machine (~125 us on C4, independent of the width), so wider is better: 1 M -> 1250, 2 M -> 1574, 4 M -> 1795,
 // 8 M -> 1903 Msamples/s.  140 bytes of state per path.
-const uint32_t kDefaultWavefront = 1u << 23;
+const uint32_t kDefaultWavefront = 1u << 24;
 
 uint32_t pick_capacity(unsigned long long total, uint32_t requested) {
   unsigned long long cap = requested ? requested : kDefaultWavefront;

@@ -93,11 +93,12 @@ def test_cuda_path_agrees_with_the_render_the_reference_ships(gpu):
     sc.close()
     assert st.samples == 800 * 800 * 4096
     ours = _box(rgb, 4)
-    d = np.abs(ours - ref).max(axis=2)
+    dc = np.abs(ours - ref)
     for name, (y0, y1, x0, x1) in REGIONS.items():
-        r = d[y0:y1, x0:x1]
+        r = dc[y0:y1, x0:x1]                       # all three channels
         print(f"{name:34s} |d| mean {r.mean():.2f}  p95 {np.percentile(r, 95):.1f}  max {r.max():.1f}  (8-bit LSBs)")
         assert r.mean() <= 1.5 and np.percentile(r, 95) <= 5.0, name
+    d = dc.max(axis=2)
     mask = _outside_drone()
     print(f"outside the drone box: mean {d[mask].mean():.2f}, within 4 LSB {np.mean(d[mask] <= 4):.3f}, within 8 LSB {np.mean(d[mask] <= 8):.3f}")
     # what is left are the drone's mirror images in the glass ball and the metallic spheres
