@@ -82,6 +82,7 @@ struct rt_scene {
   uint32_t persistent_blocks = 148 * 8;  // k_trace grid: SM count x resident blocks per SM
   // scratch for host-buffer entry points
   DevBuf d_accum, d_linear, d_rgb8, d_dbg;
+  DevBuf d_tree[3];  // ray pool of the depth-first walk (path_samples > 1)
 };
 
 namespace {
@@ -182,7 +183,13 @@ int check_camera(const rt_camera* cam) {
     return fail(RT_ERR_INVALID, "unknown CameraProjectionMode (tracing.rs:25-28)");
   if (cam->shading_mode != RT_SHADE_PATHTRACE && cam->shading_mode != RT_SHADE_PHONG)
     return fail(RT_ERR_INVALID, "unknown ShadingMode (tracing.rs:29-32)");
-  if (cam->path_samples != 1) return fail(RT_ERR_UNSUPPORTED, "path_samples must be 1 (tracing.rs:146,370)");
+  if (cam->path_samples == 0) return fail(RT_ERR_INVALID, "path_samples must be >= 1 (tracing.rs:146)");
+  if (cam->path_samples > 1 && cam->shading_mode == RT_SHADE_PATHTRACE) {
+    // every hit spawns path_samples children (tracing.rs:308-319); the position of a path in that tree keys its
+    // random numbers and must fit 32 bits
+    double nodes = std::pow((double)cam->path_samples, (double)std::max(1u, cam->path_depth) - 1.0);
+    if (nodes >= 4294967296.0) return fail(RT_ERR_UNSUPPORTED, "path_samples^(path_depth-1) must be below 2^32");
+  }
   if (cam->screen_width == 0 || cam->screen_height == 0) return fail(RT_ERR_INVALID, "empty image");
   if ((uint64_t)cam->screen_width * cam->screen_height > (1ull << 31)) return fail(RT_ERR_INVALID, "image too large");
   if (cam->aa_sample_count == 0 || cam->aa_sample_count >= (1u << 24))
@@ -226,6 +233,7 @@ void fill_frame_camera(const rt_camera& cam, uint64_t seed, rt_frame& fr) {
   fr.width = cam.screen_width;
   fr.height = cam.screen_height;
   fr.path_depth = cam.path_depth;
+  fr.path_samples = cam.shading_mode == RT_SHADE_PHONG ? 1u : cam.path_samples;  // phong_shade_ray scatters once
   fr.k0 = (uint32_t)seed;
   fr.k1 = (uint32_t)(seed >> 32);
   fr.shard_mode = RT_SHARD_ALL;
@@ -486,6 +494,94 @@ int run_wavefront(rt_scene* s, const rt_frame& fr_in, unsigned long long total, 
   return RT_OK;
 }
 
+// Camera::path_samples > 1 (tracing.rs:308-319): every hit spawns path_samples scattered rays, so a camera sample is
+// a tree of up to path_samples^(path_depth-1) paths.  The tree is walked depth first so that memory stays bounded:
+// level d holds the pending rays of bounce d; an iteration pops up to P rays from the deepest non-empty level, traces
+// them and runs k_shade once per child index, appending the children to level d+1 (which is empty at that moment and
+// can hold path_samples * P rays).  The host reads the child count back every iteration - this mode is exponential
+// in path_depth anyway and is not a bench path.
+int run_branching(rt_scene* s, const rt_frame& fr_in, unsigned long long total, long long* d_accum, cudaStream_t st,
+                  rt_stats* stats) {
+  int rc;
+  rt_frame fr = fr_in;
+  fr.sort_enabled = 0;
+  const uint64_t S = fr.path_samples, D = std::max(1u, fr.path_depth);
+  uint64_t P = std::min<uint64_t>(fr.capacity, 1u << 20);
+  while ((P + (D - 1) * S * P) * 48ull > (4ull << 30) && P > 4096) P /= 2;
+  P = std::max<uint64_t>(128, P / 128 * 128);
+  fr.capacity = (uint32_t)P;
+  if ((rc = ensure_lane(s, 0, fr.capacity)) != RT_OK) return rc;
+  const uint64_t slots = P + (D - 1) * S * P;
+  for (auto& b : s->d_tree)
+    if ((rc = ensure_buf(b, slots * 16)) != RT_OK) return rc;
+  auto level_base = [&](uint64_t d) { return d == 0 ? 0ull : P + (d - 1) * S * P; };
+  auto at = [&](uint64_t off) {
+    return rt::rt_paths{(float4*)s->d_tree[0].p + off, (float4*)s->d_tree[1].p + off, (float4*)s->d_tree[2].p + off};
+  };
+  rt_scene::Lane& L = s->lanes[0];
+  cudaEvent_t e0, e1;
+  CUDA_TRY(cudaEventCreate(&e0));
+  CUDA_TRY(cudaEventCreate(&e1));
+  CUDA_TRY(cudaEventRecord(e0, st));
+  rt::launch_init(L.ctrl, 0ull, total, st);
+  std::vector<uint64_t> pending(D, 0);
+  unsigned long long cursor = 0;
+  uint64_t launches = 1, iters = 0;
+  for (;;) {
+    int d = (int)D - 1;
+    while (d >= 0 && pending[d] == 0) --d;
+    uint32_t n_cont = 0, n_new = 0;
+    rt::rt_paths cur;
+    if (d < 0) {
+      if (cursor >= total) break;
+      d = 0;
+      n_new = (uint32_t)std::min<unsigned long long>(P, total - cursor);
+      cursor += n_new;
+      cur = at(level_base(0));
+    } else {
+      n_cont = (uint32_t)std::min<uint64_t>(pending[d], P);
+      pending[d] -= n_cont;
+      cur = at(level_base(d) + pending[d]);
+    }
+    rt::rt_paths nxt = at((uint64_t)d + 1 < D ? level_base(d + 1) : 0);  // the last level has no children
+    rt::launch_set_window(L.ctrl, n_cont, n_new, st);
+    if (n_new) rt::launch_raygen(fr, L.ctrl, cur, st);
+    rt::launch_trace(s->dev, fr, L.ctrl, cur, L.hits, L.sort, false, s->persistent_blocks, st);
+    rt::launch_sort(s->dev, fr, L.ctrl, L.hits, L.queues, st);
+    for (uint32_t b = 0; b < (uint32_t)S; ++b) {
+      fr.branch = b;
+      rt::launch_shade(s->dev, fr, L.ctrl, cur, nxt, L.hits, L.queues, d_accum, L.sort, false, st);
+    }
+    fr.branch = 0;
+    uint32_t n_next = 0;
+    CUDA_TRY(cudaMemcpyAsync(&n_next, &L.ctrl->n_next, sizeof n_next, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    if ((uint64_t)d + 1 < D) pending[d + 1] += n_next;
+    else if (n_next) return fail(RT_ERR_CUDA, "branching walk: rays survived the last level");
+    launches += 4 + S + (n_new ? 1 : 0);
+    ++iters;
+  }
+  CUDA_TRY(cudaMemcpyAsync(L.h_ctrl, L.ctrl, sizeof(rt_ctrl), cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaEventRecord(e1, st));
+  CUDA_TRY(cudaStreamSynchronize(st));
+  CUDA_TRY(cudaGetLastError());
+  if (stats) {
+    float ms = 0.0f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    const rt_ctrl& c = *L.h_ctrl;
+    stats->ms_total += ms;
+    stats->samples += c.n_samples - c.counters[7];
+    stats->rays += c.n_rays_total - c.counters[7];
+    stats->iterations += iters;
+    stats->kernel_launches += launches;
+    stats->extend_launches += iters;
+    stats->shade_launches += iters * S;
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  return RT_OK;
+}
+
 int default_lanes() {
   if (const char* e = std::getenv("RT_LANES")) return std::max(1, std::min(RT_MAX_LANES, std::atoi(e)));
   return RT_DEFAULT_LANES;
@@ -518,6 +614,7 @@ void rt_scene_destroy(rt_scene* s) {
     free_buf(s->d_nodes); free_buf(s->d_tris); free_buf(s->d_shade); free_buf(s->d_objects);
     free_buf(s->d_mats); free_buf(s->d_textures); free_buf(s->d_texels); free_buf(s->d_planes); free_buf(s->d_guards); free_buf(s->d_guard_list);
     free_buf(s->d_accum); free_buf(s->d_linear); free_buf(s->d_rgb8); free_buf(s->d_dbg);
+    for (auto& b : s->d_tree) free_buf(b);
     for (auto& L : s->lanes) {
       if (L.ctrl) cudaFree(L.ctrl);
       if (L.sort.hist) cudaFree(L.sort.hist);
@@ -795,6 +892,7 @@ int rt_render_accum(rt_scene* s, const rt_camera* cam, const rt_render_opts* opt
       fr.sort_scale[k] = ext > 0.0f ? (float)cells / ext : 0.0f;
     }
   }
+  if (fr.path_samples > 1) return run_branching(s, fr, total, (long long*)d_accum, st, stats);
   return run_wavefront(s, fr, total, (long long*)d_accum, (o.flags & RT_OPT_COUNTERS) != 0,
                        (o.flags & RT_OPT_NO_EVENTS) == 0, st, default_lanes(), stats);
 }

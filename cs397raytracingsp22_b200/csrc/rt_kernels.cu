@@ -1128,7 +1128,10 @@ __device__ __forceinline__ void accum_add(long long* accum, uint32_t pixel, f3 c
 #ifndef RT_SHADE_MIN_BLOCKS
 #define RT_SHADE_MIN_BLOCKS 10
 #endif
-template <bool COUNT>
+// MULTI (Camera::path_samples > 1): the kernel runs once per child index fr.branch over the same hits; a child's
+// random numbers are keyed by its position in the sample's path tree (carried in C.w), its throughput is divided by
+// path_samples (tracing.rs:319), and the hit's emission is added by the first pass only.
+template <bool COUNT, bool MULTI>
 __global__ void __launch_bounds__(RT_BLOCK, RT_SHADE_MIN_BLOCKS) k_shade(rt_dev_scene sc, rt_frame fr, rt_ctrl* __restrict__ ctrl,
                                                     rt_paths cur, rt_paths nxt, rt_hits hits,
                                                     const uint32_t* __restrict__ queues, long long* __restrict__ accum,
@@ -1169,7 +1172,7 @@ __global__ void __launch_bounds__(RT_BLOCK, RT_SHADE_MIN_BLOCKS) k_shade(rt_dev_
 
   bool alive = false;
   f3 no, nd, nT;
-  uint32_t pixel = 0, sb = 0;
+  uint32_t pixel = 0, sb = 0, tree = 0;
   if (j < count) {
     uint32_t slot = RT_LDS(&queues[(size_t)cls * fr.capacity + j]);
     float4 a = RT_LDS(&cur.A[slot]), bq = RT_LDS(&cur.B[slot]), c = RT_LDS(&cur.C[slot]);
@@ -1178,6 +1181,7 @@ __global__ void __launch_bounds__(RT_BLOCK, RT_SHADE_MIN_BLOCKS) k_shade(rt_dev_
     f3 T = mk(bq.z, bq.w, c.x);
     pixel = fbits(c.y);
     sb = fbits(c.z);
+    if (MULTI) tree = fbits(c.w) * fr.path_samples + fr.branch;
     uint32_t sample = sb & 0xFFFFFFu, bounce = sb >> 24;
     // hit resolution: what the reference attaches to its RayHit
     float4 hr = RT_LDS(&hits.H[slot]);
@@ -1216,10 +1220,11 @@ __global__ void __launch_bounds__(RT_BLOCK, RT_SHADE_MIN_BLOCKS) k_shade(rt_dev_
     }
 
     // emitted light reaches the pixel attenuated by the path throughput (tracing.rs:321)
-    if (emission.x != 0.0f || emission.y != 0.0f || emission.z != 0.0f) accum_add(accum, pixel, mulv(T, emission));
+    if ((!MULTI || fr.branch == 0u) && (emission.x != 0.0f || emission.y != 0.0f || emission.z != 0.0f))
+      accum_add(accum, pixel, mulv(T, emission));
 
     // scatter (materials.rs:33-166)
-    u4 r = philox4x32_10(pixel, sample, bounce, 0u, fr.k0, fr.k1);
+    u4 r = philox4x32_10(pixel, sample, bounce, 0u, fr.k0, MULTI ? fr.k1 ^ (tree * 0x9E3779B9u) : fr.k1);
     float u_choice = u01(r.x);
     f3 ball = ball_from(r.y, r.z, r.w);
     f3 dir, brdf;
@@ -1265,6 +1270,7 @@ __global__ void __launch_bounds__(RT_BLOCK, RT_SHADE_MIN_BLOCKS) k_shade(rt_dev_
     float dot_term = mag2(n) > 0.0f ? clampf(fabsf(dot(dir, n)), 0.0f, 1.0f) : 1.0f;
     f3 w = (dot_term * brdf) / pdf;
     nT = mulv(T, w);
+    if (MULTI) nT = nT / (float)fr.path_samples;
     no = hp;
     nd = dir;
     bounce += 1;
@@ -1322,7 +1328,7 @@ __global__ void __launch_bounds__(RT_BLOCK, RT_SHADE_MIN_BLOCKS) k_shade(rt_dev_
 #endif
     RT_STS(&nxt.A[pos], make_float4(no.x, no.y, no.z, nd.x));
     RT_STS(&nxt.B[pos], make_float4(nd.y, nd.z, nT.x, nT.y));
-    RT_STS(&nxt.C[pos], make_float4(nT.z, __uint_as_float(pixel), __uint_as_float(sb), 0.0f));
+    RT_STS(&nxt.C[pos], make_float4(nT.z, __uint_as_float(pixel), __uint_as_float(sb), __uint_as_float(tree)));
     if (fr.sort_enabled) {
       // one atomic per distinct key per warp: the rays of a warp mostly leave the same few cells
       uint32_t key = ray_sort_key(fr, no, nd);
@@ -1557,7 +1563,23 @@ __global__ void k_init_ctrl(rt_ctrl* c, unsigned long long begin, unsigned long 
   c->iterations = 0;
   for (int i = 0; i < 12; ++i) c->counters[i] = 0;
 }
+// Camera::path_samples > 1: the host walks the path tree depth first and tells the device what the next window is
+__global__ void k_set_window(rt_ctrl* c, uint32_t n_cont, uint32_t n_new) {
+  c->n_cont = n_cont;
+  c->n_rays = n_cont + n_new;
+  c->work_base = c->cursor;
+  c->cursor += n_new;
+  c->n_next = 0;
+  c->next_ray = 0;
+  for (int i = 0; i < RT_NUM_CLASSES; ++i) c->class_count[i] = 0;
+  c->iterations += 1;
+  c->n_rays_total += n_cont + n_new;
+  c->n_samples += n_new;
+}
 // ------------------------------------------------------------------ launchers
+void launch_set_window(rt_ctrl* ctrl, uint32_t n_cont, uint32_t n_new, cudaStream_t st) {
+  k_set_window<<<1, 1, 0, st>>>(ctrl, n_cont, n_new);
+}
 void launch_init(rt_ctrl* ctrl, unsigned long long begin, unsigned long long end, cudaStream_t st) {
   k_init_ctrl<<<1, 1, 0, st>>>(ctrl, begin, end);
 }
@@ -1599,8 +1621,9 @@ void launch_surface(const rt_dev_scene& sc, const rt_frame& fr, rt_ctrl* ctrl, r
 void launch_shade(const rt_dev_scene& sc, const rt_frame& fr, rt_ctrl* ctrl, rt_paths cur, rt_paths nxt, rt_hits hits,
                   const uint32_t* queues, long long* accum, rt_sortbuf sort, bool count, cudaStream_t st) {
   uint32_t grid = (fr.capacity + RT_BLOCK - 1) / RT_BLOCK + RT_NUM_CLASSES;
-  if (count) k_shade<true><<<grid, RT_BLOCK, 0, st>>>(sc, fr, ctrl, cur, nxt, hits, queues, accum, sort);
-  else k_shade<false><<<grid, RT_BLOCK, 0, st>>>(sc, fr, ctrl, cur, nxt, hits, queues, accum, sort);
+  if (fr.path_samples > 1) k_shade<false, true><<<grid, RT_BLOCK, 0, st>>>(sc, fr, ctrl, cur, nxt, hits, queues, accum, sort);
+  else if (count) k_shade<true, false><<<grid, RT_BLOCK, 0, st>>>(sc, fr, ctrl, cur, nxt, hits, queues, accum, sort);
+  else k_shade<false, false><<<grid, RT_BLOCK, 0, st>>>(sc, fr, ctrl, cur, nxt, hits, queues, accum, sort);
 }
 void launch_phong_primary(const rt_dev_scene& sc, const rt_frame& fr, rt_ctrl* ctrl, rt_paths cur, rt_paths nxt, rt_hits hits,
                           cudaStream_t st) {

@@ -48,6 +48,7 @@ void launch_surface(const rt_dev_scene& sc, const rt_frame& fr, rt_ctrl* ctrl, r
 int trace_blocks_per_sm();
 void launch_shade(const rt_dev_scene& sc, const rt_frame& fr, rt_ctrl* ctrl, rt_paths cur, rt_paths nxt, rt_hits hits,
                   const uint32_t* queues, long long* accum, rt_sortbuf sort, bool count, cudaStream_t st);
+void launch_set_window(rt_ctrl* ctrl, uint32_t n_cont, uint32_t n_new, cudaStream_t st);
 void launch_phong_primary(const rt_dev_scene& sc, const rt_frame& fr, rt_ctrl* ctrl, rt_paths cur, rt_paths nxt, rt_hits hits,
                           cudaStream_t st);
 void launch_phong_shadow(const rt_dev_scene& sc, const rt_frame& fr, rt_ctrl* ctrl, rt_paths cur, rt_hits hits, long long* accum,

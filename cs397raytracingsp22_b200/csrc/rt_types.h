@@ -106,6 +106,7 @@ struct rt_frame {
   unsigned long long pixel_slots;   // pixel slots of this shard (work items = pixel_slots * sample_count)
   uint32_t capacity;                // wavefront width P
   // debug modes of the reference: orthographic projection (tracing.rs:196,200), Phong shading (tracing.rs:277-297)
+  uint32_t path_samples, branch;    // Camera::path_samples > 1 (tracing.rs:146,308-319): child index of this k_shade pass
   uint32_t phong;                   // host-side switch: camera ray + shadow ray pairs instead of path iterations
   uint32_t ortho, ray_tmax_from_c;  // ray_tmax_from_c: a ray's own t_max travels in C.w (Phong shadow rays)
   float view_dir[3], light[3], ambient[3];

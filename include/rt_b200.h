@@ -73,7 +73,7 @@ typedef struct rt_camera {
   uint32_t projection_mode; /* RT_PROJ_ORTHOGRAPHIC is the reference's debug projection (tracing.rs:196,200) */
   uint32_t shading_mode;    /* RT_SHADE_PHONG is the reference's debug shading (tracing.rs:277-297)          */
   uint32_t path_depth;
-  uint32_t path_samples; /* must be 1 (tracing.rs:146,370) */
+  uint32_t path_samples; /* scattered rays per hit (tracing.rs:146,308-319); > 1 walks the path tree depth first */
   uint32_t screen_width;
   uint32_t screen_height;
   float focal_length;

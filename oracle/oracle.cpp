@@ -738,18 +738,28 @@ struct RenderCtx {
   uint32_t k0, k1;
 };
 
-// Scene::shade_ray, tracing.rs:300-324 (path_samples == 1)
-V3 shade_ray(const RenderCtx& c, const Ray& ray, uint32_t depth, const RngKey& key, Counters* cnt) {
+// Scene::shade_ray, tracing.rs:300-324.  `tree` is the position of this path in the sample's tree of scattered rays
+// (child b of node t is t * path_samples + b; always 0 when path_samples == 1): it keys the scatter draws of the
+// children so that siblings get different random numbers.  Volume free-path draws are keyed by (pixel, sample,
+// bounce) alone, i.e. siblings share them - unbiased, and it keeps the closest-hit kernel free of tree bookkeeping.
+V3 shade_ray(const RenderCtx& c, const Ray& ray, uint32_t depth, const RngKey& key, Counters* cnt, uint32_t tree = 0) {
   if (depth >= c.cam.path_depth) return v3(0, 0, 0);
   Hit hit;
   if (!scene_hit(*c.sc, ray, 0.001f, c.cam.max_trace_dist, c.mode, key, depth, hit, cnt)) return v3(0, 0, 0);
   const rt_material_desc& m = hit.material >= 0 ? c.sc->materials[hit.material].d : hit.param;
-  U4 r = draw(key, depth, 0);
-  Scatter s = scatter(m, hit, ray, r);
-  float dot_term = mag2(hit.normal) > 0.0f ? rclamp(std::fabs(dot(s.ray.direction, hit.normal)), 0.0f, 1.0f) : 1.0f;
-  V3 incoming = shade_ray(c, s.ray, depth + 1, key, cnt);
-  V3 integral = (dot_term * mul_elem(s.brdf, incoming)) / s.pdf;
-  integral = integral / 1.0f;  // path_samples
+  const uint32_t S = c.cam.path_samples;
+  V3 integral = v3(0, 0, 0);
+  for (uint32_t b = 0; b < S; ++b) {  // tracing.rs:308-318
+    uint32_t child = tree * S + b;
+    RngKey ck = key;
+    ck.k1 ^= child * 0x9E3779B9u;
+    U4 r = draw(ck, depth, 0);
+    Scatter s = scatter(m, hit, ray, r);
+    float dot_term = mag2(hit.normal) > 0.0f ? rclamp(std::fabs(dot(s.ray.direction, hit.normal)), 0.0f, 1.0f) : 1.0f;
+    V3 incoming = shade_ray(c, s.ray, depth + 1, key, cnt, child);
+    integral = integral + (dot_term * mul_elem(s.brdf, incoming)) / s.pdf;
+  }
+  integral = integral / (float)S;  // tracing.rs:319
   V3 emission = m.tag == RT_MAT_DIELECTRIC ? v3(0, 0, 0) : v3(m.emission[0], m.emission[1], m.emission[2]);
   return emission + integral;
 }
@@ -837,7 +847,7 @@ inline void output_transform(V3 mean, float gamma, uint8_t* rgb) {
 inline int check_camera(const rt_camera* cam) {
   if (!cam) return RT_ERR_INVALID;
   if (cam->projection_mode > RT_PROJ_PERSPECTIVE || cam->shading_mode > RT_SHADE_PATHTRACE) return RT_ERR_INVALID;
-  if (cam->path_samples != 1) return RT_ERR_UNSUPPORTED;
+  if (cam->path_samples == 0) return RT_ERR_INVALID;
   if (cam->screen_width == 0 || cam->screen_height == 0 || cam->aa_sample_count == 0) return RT_ERR_INVALID;
   return RT_OK;
 }

@@ -139,10 +139,13 @@ def test_empty_and_degenerate_inputs(gpu):
     a, b = g2.trace_primary(cam.to_c(), 1, 0), o2.trace_primary(cam.to_c(), 1, 0)
     assert np.array_equal(a["obj"], b["obj"]) and not (a["obj"] == 0).any() and (a["obj"] == 1).any()
     # unsupported settings are refused, not approximated
-    two = rt.Camera(path_samples=2)
+    big = rt.Camera(path_samples=100, path_depth=10)          # 100^9 paths per camera sample
     with pytest.raises(_ffi.RtError) as e:
-        g.render(two.to_c())
+        g.render(big.to_c())
     assert e.value.code == _ffi.RT_ERR_UNSUPPORTED
+    with pytest.raises(_ffi.RtError) as e:
+        g.render(rt.Camera(path_samples=0).to_c())
+    assert e.value.code == _ffi.RT_ERR_INVALID
 
 
 def _render_pair(sc, spp_kw=None):
@@ -267,6 +270,52 @@ def test_orthographic_path_tracing_and_primary_hits(gpu):
     scale = max(float(lin_o.mean()), 1e-6)
     assert np.median(diff) <= 1e-5 * max(scale, 1.0)
     assert (diff.max(axis=2) > 1e-3 * np.maximum(lin_o.max(axis=2), scale)).mean() < 0.03
+
+
+@pytest.mark.parametrize("name,samples,depth", [("c1", 2, 4), ("c4", 3, 3), ("c2", 2, 5)])
+def test_branching_paths_match_the_oracle(gpu, small_scenes, name, samples, depth):
+    """Camera::path_samples > 1 (tracing.rs:308-319): every hit scatters path_samples rays.  Both sides key a child by
+    its position in the tree, so the images track each other sample for sample like the unbranched ones do."""
+    kw = dict(width=48, height=48, spp=16, depth=depth)
+    if name == "c4":
+        kw.update(width=64, height=36, map_size=128)
+    sc = small_scenes(name, **kw)
+    sc.camera.path_samples = samples
+    try:
+        lin_g, rgb_g, st_g, lin_o, rgb_o, st_o = _render_pair(sc)
+    finally:
+        sc.camera.path_samples = 1                     # the scene object is shared through the session cache
+    assert st_g.samples == st_o.samples
+    per_sample = sum(samples ** k for k in range(depth))
+    assert st_o.rays <= st_o.samples * per_sample and st_g.rays <= st_o.rays * 1.001 and st_g.rays >= 0.9 * st_o.rays
+    assert st_o.rays > st_o.samples * 2                # it did branch
+    diff = np.abs(lin_g - lin_o)
+    scale = max(float(lin_o.mean()), 1e-6)
+    assert np.median(diff) <= 1e-5 * max(scale, 1.0)
+    bad = (diff.max(axis=2) > 1e-3 * np.maximum(lin_o.max(axis=2), scale)).mean()
+    assert bad < 0.05, f"{name}: {bad:.4f} of pixels decorrelated"
+    assert abs(float(lin_g.mean()) - float(lin_o.mean())) <= 3e-3 * scale
+
+
+def test_branching_is_unbiased_and_walks_depth_first_in_bounded_memory(gpu, small_scenes):
+    """path_samples only changes the variance: the mean image of 2-way branching equals the unbranched one.  The walk
+    is depth first with a small window, so 3^5 leaves per camera sample never exist at the same time."""
+    sc = small_scenes("c1", width=32, height=32, spp=256, depth=6)
+    g = sc.commit(0)
+    o = _ffi.rt_render_opts(); o.seed = SEED
+    lin1, _, st1 = g.render(sc.camera.to_c(), o)
+    sc.camera.path_samples = 3
+    try:
+        o.wavefront = 8192                             # force many windows and deep stacks
+        lin3, _, st3 = g.render(sc.camera.to_c(), o)
+        o.wavefront = 0
+        lin3b, _, _ = g.render(sc.camera.to_c(), o)
+    finally:
+        sc.camera.path_samples = 1
+    assert st3.rays > 20 * st1.rays and st3.iterations > 100
+    assert np.array_equal(lin3, lin3b)                 # the window size does not change the result
+    m1, m3 = float(lin1.mean()), float(lin3.mean())
+    assert abs(m1 - m3) <= 0.02 * m1, (m1, m3)
 
 
 def test_furnace_on_the_gpu(gpu):
