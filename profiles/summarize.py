@@ -12,7 +12,9 @@ METRICS = [
     "smsp__issue_active.avg.pct_of_peak_sustained_active", "smsp__inst_executed.sum",
     "smsp__thread_inst_executed_per_inst_executed.ratio", "l1tex__t_sector_hit_rate.pct", "lts__t_sector_hit_rate.pct",
     "dram__bytes_read.sum", "dram__bytes_write.sum", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
-    "lts__t_bytes.sum", "l1tex__t_bytes.sum", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
+    "lts__t_bytes.sum", "l1tex__t_bytes.sum", "l1tex__t_sectors_pipe_lsu_mem_global_op_ld.sum", "l1tex__throughput.avg.pct_of_peak_sustained_elapsed",
+    "lts__t_sectors.sum", "lts__t_sectors.sum.per_second", "lts__throughput.avg.pct_of_peak_sustained_elapsed",
+    "lts__t_sector_op_read_hit_rate.pct", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
     "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active",
 ]
 STALLS = ["long_scoreboard", "wait", "barrier", "not_selected", "math_pipe_throttle", "branch_resolving", "short_scoreboard",
