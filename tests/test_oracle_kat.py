@@ -269,3 +269,79 @@ def test_mesh_hit_frame(small_scenes):
     assert np.allclose(np.linalg.norm(n, axis=1), 1.0, atol=1e-5)
     d = r["ray"][mesh, 3:]
     assert ((n * d).sum(axis=1) < 1e-6).all()
+
+
+def test_furnace_with_branching_paths():
+    """Camera::path_samples = S (tracing.rs:308-319) changes the variance, not the expectation: the furnace value
+    is the same, and a closed scene costs 1 + S + S^2 + ... closest-hit queries per camera sample."""
+    a, e, depth, S = 0.5, 1.0, 4, 3
+    cam = rt.Camera(eyepoint=(0, 0, 0), screen_width=16, screen_height=16, aa_sample_count=256, path_depth=depth, path_samples=S)
+    sc = rt.Scene(camera=cam, objects=[rt.Sphere((0, 0, 0), 10.0, rt.Lambertian(albedo=(a,) * 3, emission=(e,) * 3))])
+    lin, _, st = O.lower_to_oracle(sc).render(cam.to_c(), seed=9)
+    want = e * (1 - (0.75 * a) ** depth) / (1 - 0.75 * a)
+    assert abs(lin.mean() - want) < 4e-3
+    per_sample = sum(S ** k for k in range(depth))
+    assert 0.99 * st.samples * per_sample < st.rays <= st.samples * per_sample
+    cam.path_samples = 1
+    lin1, _, st1 = O.lower_to_oracle(sc).render(cam.to_c(), seed=9)
+    assert lin.std() < lin1.std()                      # more scattered rays per hit: less noise per camera sample
+
+
+def _phong_value(objects, light=(0.0, 2.0, 0.0), ambient=(0.05, 0.1, 0.15)):
+    """Looks at the origin of the plane y = 0 from (3, 1, 0) through a very long lens: every pixel shades (nearly) the
+    same point, n = (0,1,0), to_light = (0,1,0), and the mirror direction is 71.6 degrees away from the camera."""
+    v = np.array([-3.0, -1.0, 0.0]) / math.sqrt(10.0)
+    up = np.array([-1.0, 3.0, 0.0]) / math.sqrt(10.0)
+    cam = rt.Camera(eyepoint=(3, 1, 0), view_dir=tuple(v), up=tuple(up), focal_length=400.0, screen_width=9, screen_height=9,
+                    aa_sample_count=4, shading_mode=rt.ShadingMode.Phong)
+    sc = rt.Scene(camera=cam, objects=objects, point_light_pos=light, ambient=ambient)
+    lin, _, st = O.lower_to_oracle(sc).render(cam.to_c(), seed=5)
+    assert lin.reshape(-1, 3).std(axis=0).max() < 2e-3
+    return lin.reshape(-1, 3).mean(axis=0), st
+
+
+def test_phong_shading_known_answers():
+    """Scene::phong_shade_ray (tracing.rs:277-297): ambient + diffuse * brdf + specular^40 * 0.4, times 0.3 when the
+    shadow ray is blocked - but only by an occluder that is nearer to the shaded point than to the light (`:292`)."""
+    a = (0.8, 0.5, 0.2)
+    amb = np.array([0.05, 0.1, 0.15])
+    floor = rt.Plane(point=(0, 0, 0), normal=(0, 1, 0), material=rt.Lambertian(albedo=a))
+    lit = amb + np.array(a) / math.pi                  # diffuse weight 1, specular weight (1/sqrt(10))^40 ~ 1e-20
+    got, st = _phong_value([floor])
+    assert np.allclose(got, lit, atol=1e-3)
+    assert st.rays == 2 * st.samples                   # one camera ray + one shadow ray
+    # an occluder close to the surface: shadow weight 0.3
+    got, _ = _phong_value([floor, rt.Sphere((0, 0.5, 0), 0.2, rt.Lambertian())])
+    assert np.allclose(got, 0.3 * lit, atol=1e-3)
+    # the same occluder close to the light: hit.distance^2 > |light - hit|^2, so the reference does not darken
+    got, _ = _phong_value([floor, rt.Sphere((0, 1.5, 0), 0.2, rt.Lambertian())])
+    assert np.allclose(got, lit, atol=1e-3)
+    # metal: the brdf term of scatter() is the albedo itself (materials.rs:64)
+    got, _ = _phong_value([rt.Plane(point=(0, 0, 0), normal=(0, 1, 0), material=rt.Metal(albedo=a, roughness=0.3))])
+    assert np.allclose(got, amb + np.array(a), atol=1e-3)
+    # light in the mirror direction of the camera: specular weight 1
+    got, _ = _phong_value([floor], light=(-6.0, 2.0, 0.0))
+    n_dot_l = 2.0 / math.sqrt(40.0)
+    assert np.allclose(got, amb + n_dot_l * np.array(a) / math.pi + 0.4, atol=2e-3)
+    # nothing hit: black, and no shadow ray
+    got, st = _phong_value([rt.Sphere((0, 50, 0), 1.0, rt.Lambertian())])
+    assert np.all(got == 0) and st.rays == st.samples
+
+
+def test_orthographic_projection_as_the_reference_writes_it():
+    """CameraProjectionMode::Orthographic (tracing.rs:196,200): the ray starts at the camera-space pixel centre taken
+    as a WORLD point (z = 0, the eyepoint is ignored) and runs along rotation * view_dir."""
+    cam = rt.Camera(eyepoint=(7, 8, 9), screen_width=32, screen_height=16, aa_sample_count=4,
+                    projection_mode=rt.CameraProjectionMode.Orthographic)
+    sc = rt.Scene(camera=cam, objects=[rt.Sphere((0, 0, -3), 0.25, rt.Lambertian())])
+    o = O.lower_to_oracle(sc)
+    p = o.trace_primary(cam.to_c(), 1, 0)
+    ray = p["ray"].reshape(16, 32, 6)
+    assert np.all(ray[..., 2] == 0.0)
+    assert np.all(ray[..., 3:] == np.array([0, 0, -1], np.float32))    # rotation * view_dir = view_dir for this basis
+    ps = 1.0 / 16
+    assert abs(ray[0, 0, 0] - (-1.0 + 0.5 * ps)) <= ps and abs(ray[0, 31, 0] - (1.0 - 0.5 * ps)) <= ps
+    assert abs(ray[0, 0, 1] - 0.5) <= 1.5 * ps and abs(ray[15, 0, 1] + 0.5) <= 1.5 * ps
+    # the sphere of radius 0.25 covers pi r^2 of the 2 x 1 window, wherever the eyepoint is
+    frac = (p["obj"] == 0).mean()
+    assert abs(frac - math.pi * 0.25 ** 2 / 2.0) < 0.02
