@@ -28,13 +28,15 @@ struct Huffman {
   uint8_t vals[256];
   int mincode[17], maxcode[18], valptr[17];
   uint8_t look_len[256], look_val[256];  // codes of up to 8 bits resolved in one step
-  void build(const uint8_t counts[16], const uint8_t* symbols) {
-    present = true;
+  // false: the code lengths over-subscribe the code space (not a prefix code)
+  bool build(const uint8_t counts[16], const uint8_t* symbols) {
+    present = false;
     int code = 0, k = 0;
     std::memset(look_len, 0, sizeof look_len);
     for (int len = 1; len <= 16; ++len) {
       valptr[len] = k;
       mincode[len] = code;
+      if (code + counts[len - 1] > (1 << len)) return false;
       for (int i = 0; i < counts[len - 1]; ++i, ++k, ++code) {
         vals[k] = symbols[k];
         if (len <= 8) {
@@ -49,6 +51,8 @@ struct Huffman {
       code <<= 1;
     }
     maxcode[17] = 0x7FFFFFFF;
+    present = true;
+    return true;
   }
 };
 
@@ -171,7 +175,7 @@ struct Decoder {
       int total = 0;
       for (int i = 0; i < 16; ++i) total += p[1 + i];
       if (total > 256 || n < 17 + total) return bad("bad Huffman table");
-      (tc ? ac[th] : dc[th]).build(p + 1, p + 17);
+      if (!(tc ? ac[th] : dc[th]).build(p + 1, p + 17)) return bad("Huffman table is not a prefix code");
       p += 17 + total;
       n -= 17 + total;
     }

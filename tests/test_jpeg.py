@@ -53,3 +53,28 @@ def test_bad_input_is_an_error_not_a_crash():
     img = _ffi.jpeg_decode(good[:len(good) - 40])
     assert img.shape == (29, 37, 3)
     assert Texture.load_from_file(os.path.join(JPEG, "does_not_exist.jpg")) is None
+
+
+def test_mutated_files_never_crash_the_readers():
+    """A light version of tools/fuzz_decoders.cpp (which runs under ASan/UBSan): a corrupted file either decodes to an
+    image of the announced size or raises RtError."""
+    rng = np.random.default_rng(2024)
+    seeds = [open(f, "rb").read() for f in FILES] + [open(scenes.tex_path("green.png"), "rb").read()]
+    for data in seeds:
+        png = data[:4] == b"\x89PNG"
+        for _ in range(150):
+            d = bytearray(data)
+            for _ in range(int(rng.integers(1, 6))):
+                pos = int(rng.integers(0, len(d)))
+                op = int(rng.integers(0, 3))
+                if op == 0:
+                    d[pos] = int(rng.integers(0, 256))
+                elif op == 1:
+                    d[pos] ^= 1 << int(rng.integers(0, 8))
+                elif len(d) > 32:
+                    del d[int(rng.integers(16, len(d))):]
+            try:
+                img = (_ffi.png_decode if png else _ffi.jpeg_decode)(bytes(d))
+            except _ffi.RtError:
+                continue
+            assert img.ndim == 3 and img.shape[2] == 3 and img.size > 0
