@@ -863,6 +863,8 @@ int rt_render_accum(rt_scene* s, const rt_camera* cam, const rt_render_opts* opt
   fr.capacity = pick_capacity(total, o.wavefront);
   if (stats) std::memset(stats, 0, sizeof *stats);
   if (total == 0) return RT_OK;
+  // path_depth == 0: shade_ray returns the (black) background before it looks for a hit (tracing.rs:301-303)
+  if (cam->shading_mode == RT_SHADE_PATHTRACE && cam->path_depth == 0) return RT_OK;
   if ((rc = ensure_runtime(s)) != RT_OK) return rc;
   // NULL means the (legacy) default stream, as documented: work must be ordered after whatever the caller has
   // already enqueued there (e.g. the memset of d_accum), which a private non-blocking stream would not be
