@@ -353,9 +353,11 @@ def main():
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
     achieved = alg_bytes / (ext_ms * 1e-3) / 1e9 if ext_ms > 0 else 0.0
-    traffic = None
+    traffic, ncu_counters = None, None
     try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "k_trace_dram_traffic.json"))).get(args.workload)
+        prof = json.load(open(os.path.join(ROOT, "profiles", "k_trace_dram_traffic.json")))
+        traffic = prof.get(args.workload)
+        ncu_counters = prof.get(args.workload + "_ncu")   # what actually bounds the kernel (one ncu --set full capture)
     except Exception:
         pass
     roofline = {
@@ -370,6 +372,7 @@ def main():
         "tlas_nodes_per_ray": counted["tlas_nodes_visited"] / max(counted["rays"], 1),
         "tris_per_ray": counted["tris_tested"] / max(counted["rays"], 1),
         "traversal_simt_efficiency": counted["nodes_visited"] / max(counted["warp_node_slots"], 1),
+        "ncu": ncu_counters,
         "note": "the lowered scene fits in L2, so DRAM traffic is far below algorithmic bytes; the kernel is "
                 "latency/issue bound (see profiles/)",
     }
