@@ -35,17 +35,11 @@ namespace rt {
 #define RT_SMEM_STACK 16   // traversal-stack entries per thread kept in shared memory
 #endif
 #define RT_LOCAL_STACK 48  // overflow entries (local memory; host checks depth <= 62)
-#ifndef RT_STACK_DIST
-#define RT_STACK_DIST 0
-#endif
 // RT_STREAM_HINTS: ray queue / hit record traffic uses the streaming (evict-first) cache operators so that it does
-// not push BVH nodes, triangles and texels out of L1/L2.  RT_PREFETCH_FAR: prefetch the children of the child that
-// is pushed on the stack.
+// not push BVH nodes, triangles and texels out of L1/L2.  (Tried and dropped, profiles/r1_notes.md B2, B6: stack
+// entries that carry their entry distance, and prefetching the children of the pushed child.)
 #ifndef RT_STREAM_HINTS
 #define RT_STREAM_HINTS 1
-#endif
-#ifndef RT_PREFETCH_FAR
-#define RT_PREFETCH_FAR 0
 #endif
 #if RT_STREAM_HINTS
 #define RT_LDS(p) __ldcs(p)
@@ -56,8 +50,6 @@ namespace rt {
 #endif
 #ifndef RT_OCTANT_SORT
 #define RT_OCTANT_SORT 1
-#endif
-#ifndef RT_SHADE_BLOCK_NOTE
 #endif
 #ifndef RT_EXTEND_MIN_BLOCKS
 #define RT_EXTEND_MIN_BLOCKS 8  // 64 registers per thread -> 32 resident warps per SM
@@ -295,45 +287,18 @@ struct Trav {
     wd = mk(a.w, b.x, b.y);
   }
 
-#if RT_STACK_DIST
-  // every entry carries the distance at which the ray enters its box, so that an entry that has fallen behind the
-  // closest hit found since it was pushed is discarded without fetching its children (8-byte entries)
-  __device__ __forceinline__ void push(uint32_t v, float tn = 0.0f) {
-    if (sp < RT_SMEM_STACK)
-      asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(sbase + (uint32_t)sp * (RT_BLOCK * 8u)), "r"(v), "r"(__float_as_uint(tn)) : "memory");
-    else {
-      lstack[2 * (sp - RT_SMEM_STACK)] = v;
-      lstack[2 * (sp - RT_SMEM_STACK) + 1] = __float_as_uint(tn);
-    }
-    ++sp;
-  }
-  __device__ __forceinline__ uint32_t pop(float& tn) {
-    --sp;
-    uint32_t v, w;
-    if (sp < RT_SMEM_STACK)
-      asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v), "=r"(w) : "r"(sbase + (uint32_t)sp * (RT_BLOCK * 8u)) : "memory");
-    else {
-      v = lstack[2 * (sp - RT_SMEM_STACK)];
-      w = lstack[2 * (sp - RT_SMEM_STACK) + 1];
-    }
-    tn = __uint_as_float(w);
-    return v;
-  }
-#else
-  __device__ __forceinline__ void push(uint32_t v, float = 0.0f) {
+  __device__ __forceinline__ void push(uint32_t v) {
     if (sp < RT_SMEM_STACK) asm volatile("st.shared.u32 [%0], %1;" ::"r"(sbase + (uint32_t)sp * (RT_BLOCK * 4u)), "r"(v) : "memory");
     else lstack[sp - RT_SMEM_STACK] = v;
     ++sp;
   }
-  __device__ __forceinline__ uint32_t pop(float& tn) {
+  __device__ __forceinline__ uint32_t pop() {
     --sp;
     uint32_t v;
     if (sp < RT_SMEM_STACK) asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(sbase + (uint32_t)sp * (RT_BLOCK * 4u)) : "memory");
     else v = lstack[sp - RT_SMEM_STACK];
-    tn = 0.0f;
     return v;
   }
-#endif
   __device__ __forceinline__ void set_space(f3 no, f3 nd) {
     o = no; d = nd;
     inv = approx_inv(d);
@@ -374,8 +339,7 @@ struct Trav {
   template <bool VOLMESH>
   __device__ __forceinline__ bool pop_next() {
     if (sp == 0) return false;
-    float tn;
-    entry = pop(tn);
+    entry = pop();
     if (VOLMESH && entry == RT_ENTRY_VOLRET) {
       volret = true;
       entry = RT_ENTRY_NONE;
@@ -387,9 +351,6 @@ struct Trav {
       in_blas = false;
       entry = RT_ENTRY_NONE;
     }
-#if RT_STACK_DIST
-    else if (tn > best.t) entry = RT_ENTRY_NONE;  // fell behind the closest hit: drop it, the caller pops again
-#endif
     return true;
   }
 };
@@ -443,12 +404,8 @@ __device__ __forceinline__ void trav_interior(const rt_dev_scene& sc, Trav& T) {
   if (hl && hr) {
     bool lfirst = tl <= tr;
     uint32_t far = lfirst ? er : el;
-    T.push(far, lfirst ? tr : tl);
+    T.push(far);
     T.entry = lfirst ? el : er;
-#if RT_PREFETCH_FAR
-    if (!(far & RT_LEAF_FLAG))
-      asm volatile("prefetch.global.L1 [%0];" ::"l"(reinterpret_cast<const float4*>(sc.nodes) + (size_t)far * 2u));
-#endif
   } else {
     T.entry = hl ? el : (hr ? er : RT_ENTRY_NONE);
   }
@@ -892,15 +849,15 @@ __global__ void __launch_bounds__(RT_BLOCK) k_raygen(rt_frame fr, rt_ctrl* __res
 template <bool COUNT, bool VOLMESH>
 __global__ void __launch_bounds__(RT_BLOCK, RT_EXTEND_MIN_BLOCKS) k_trace(rt_dev_scene sc, rt_frame fr, rt_ctrl* __restrict__ ctrl,
                                                                         rt_paths cur, rt_hits hits, const uint32_t* __restrict__ order) {
-  __shared__ __align__(8) uint32_t sstack[(RT_SMEM_STACK * (RT_STACK_DIST ? 2 : 1) + 6 + (VOLMESH ? 6 : 0)) * RT_BLOCK];
+  __shared__ __align__(8) uint32_t sstack[(RT_SMEM_STACK + 6 + (VOLMESH ? 6 : 0)) * RT_BLOCK];
   const uint32_t n_rays = ctrl->n_rays;
   const uint32_t n_sorted = fr.sort_enabled ? ctrl->n_cont : 0u;  // continuing rays are visited in sorted order
   const uint32_t lane = threadIdx.x & 31u;
   const uint32_t FULL = 0xFFFFFFFFu;
-  uint32_t lstack[RT_LOCAL_STACK * (RT_STACK_DIST ? 2 : 1)];
+  uint32_t lstack[RT_LOCAL_STACK];
   Trav T;
-  T.sbase = (uint32_t)__cvta_generic_to_shared(sstack) + threadIdx.x * (RT_STACK_DIST ? 8u : 4u);
-  T.wbase = (uint32_t)__cvta_generic_to_shared(sstack) + RT_SMEM_STACK * (RT_STACK_DIST ? 2u : 1u) * (RT_BLOCK * 4u) + threadIdx.x * 4u;
+  T.sbase = (uint32_t)__cvta_generic_to_shared(sstack) + threadIdx.x * 4u;
+  T.wbase = (uint32_t)__cvta_generic_to_shared(sstack) + RT_SMEM_STACK * (RT_BLOCK * 4u) + threadIdx.x * 4u;
   T.lstack = lstack;
   T.t_min = fr.t_min; T.t_max = fr.t_max;
   T.k0 = fr.k0; T.k1 = fr.k1;
