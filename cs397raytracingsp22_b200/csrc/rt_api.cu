@@ -92,6 +92,20 @@ void free_buf(DevBuf& b) {
   b.p = nullptr;
   b.bytes = 0;
 }
+// two timing events that do not outlive an early error return
+struct EventPair {
+  cudaEvent_t a = nullptr, b = nullptr;
+  int create() {
+    CUDA_TRY(cudaEventCreate(&a));
+    CUDA_TRY(cudaEventCreate(&b));
+    return RT_OK;
+  }
+  ~EventPair() {
+    if (a) cudaEventDestroy(a);
+    if (b) cudaEventDestroy(b);
+  }
+};
+
 int ensure_buf(DevBuf& b, size_t bytes) {
   if (b.bytes >= bytes && b.p) return RT_OK;
   free_buf(b);
@@ -519,9 +533,9 @@ int run_branching(rt_scene* s, const rt_frame& fr_in, unsigned long long total, 
     return rt::rt_paths{(float4*)s->d_tree[0].p + off, (float4*)s->d_tree[1].p + off, (float4*)s->d_tree[2].p + off};
   };
   rt_scene::Lane& L = s->lanes[0];
-  cudaEvent_t e0, e1;
-  CUDA_TRY(cudaEventCreate(&e0));
-  CUDA_TRY(cudaEventCreate(&e1));
+  EventPair ev;
+  if ((rc = ev.create()) != RT_OK) return rc;
+  cudaEvent_t e0 = ev.a, e1 = ev.b;
   CUDA_TRY(cudaEventRecord(e0, st));
   rt::launch_init(L.ctrl, 0ull, total, st);
   std::vector<uint64_t> pending(D, 0);
@@ -577,8 +591,6 @@ int run_branching(rt_scene* s, const rt_frame& fr_in, unsigned long long total, 
     stats->extend_launches += iters;
     stats->shade_launches += iters * S;
   }
-  cudaEventDestroy(e0);
-  cudaEventDestroy(e1);
   return RT_OK;
 }
 
@@ -931,9 +943,9 @@ int rt_render(rt_scene* s, const rt_camera* cam, const rt_render_opts* opts, flo
   unsigned long long total = 0;
   if ((rc = plan_shard(*cam, o, fr, total)) != RT_OK) return rc;
   uint32_t spp = total ? fr.sample_count : 1;
-  cudaEvent_t e0, e1;
-  CUDA_TRY(cudaEventCreate(&e0));
-  CUDA_TRY(cudaEventCreate(&e1));
+  EventPair ev;
+  if ((rc = ev.create()) != RT_OK) return rc;
+  cudaEvent_t e0 = ev.a, e1 = ev.b;
   if (out_linear && (rc = ensure_buf(s->d_linear, npix * 12)) != RT_OK) return rc;
   if (out_rgb8 && (rc = ensure_buf(s->d_rgb8, npix * 3)) != RT_OK) return rc;
   CUDA_TRY(cudaEventRecord(e0, st));
@@ -953,8 +965,6 @@ int rt_render(rt_scene* s, const rt_camera* cam, const rt_render_opts* opts, flo
   float ms = 0.0f;
   cudaEventElapsedTime(&ms, e0, e1);
   local.ms_resolve = ms;
-  cudaEventDestroy(e0);
-  cudaEventDestroy(e1);
   local.h2d_bytes += sizeof(rt_frame) + sizeof(rt_dev_scene);  // kernel parameters
   local.d2h_bytes += sizeof(rt_ctrl);
   if (stats) *stats = local;
