@@ -18,6 +18,7 @@ _LIB = None
 RT_OK = 0
 RT_ERR_INVALID, RT_ERR_UNSUPPORTED, RT_ERR_CUDA, RT_ERR_IO, RT_ERR_NOT_COMMITTED = -1, -2, -3, -4, -5
 RT_MAT_LAMBERTIAN, RT_MAT_METAL, RT_MAT_DIELECTRIC, RT_MAT_PARAMETERIZED, RT_MAT_ISOTROPIC = range(5)
+RT_B200_ABI_VERSION = 2  # include/rt_b200.h
 RT_PROJ_ORTHOGRAPHIC, RT_PROJ_PERSPECTIVE = 0, 1
 RT_SHADE_PHONG, RT_SHADE_PATHTRACE = 0, 1
 RT_SHARD_ALL, RT_SHARD_SAMPLES, RT_SHARD_TILES = 0, 1, 2

@@ -45,6 +45,7 @@ def build(force: bool = False, verbose: bool = False, defines: tuple = (), out: 
     out = out or LIB
     if not force and not needs_build() and out == LIB:
         return LIB
+    tmp = f"{out}.tmp{os.getpid()}"  # written aside and renamed: a process that has the old library mapped keeps it
     cmd = [
         _nvcc(), *_host_cxx(),
         "-gencode", "arch=compute_100a,code=sm_100a",
@@ -52,7 +53,7 @@ def build(force: bool = False, verbose: bool = False, defines: tuple = (), out: 
         "-fmad=false",
         "-Xcompiler", "-fPIC,-ffp-contract=off,-fno-fast-math,-O3",
         *[f"-D{d}" for d in defines],
-        "-shared", "-o", out,
+        "-shared", "-o", tmp,
         *[os.path.join(CSRC, f) for f in SOURCES],
     ]
     if verbose:
@@ -60,7 +61,10 @@ def build(force: bool = False, verbose: bool = False, defines: tuple = (), out: 
         print(" ".join(cmd), file=sys.stderr)
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
+        if os.path.exists(tmp):
+            os.remove(tmp)
         raise RuntimeError("nvcc failed:\n" + r.stdout + r.stderr)
+    os.replace(tmp, out)
     if verbose:
         print(r.stderr, file=sys.stderr)
     return out

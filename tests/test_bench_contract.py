@@ -55,3 +55,14 @@ def test_header_and_binding_agree_on_the_abi():
     declared = set(re.findall(r"\b(rt_[a-z0-9_]+)\s*\(", re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)))
     assert declared == set(_ffi.SIGNATURES)
     assert len(declared) == 34
+
+
+def test_graft_entry_build_runs_here():
+    """The driver calls __graft_entry__.build() on a box without a GPU: nvcc cross-compiles the library for sm_100a, g++
+    builds the oracle, and the ABI version of the result matches the header and the binding."""
+    import __graft_entry__ as g
+    g.build()
+    from cs397raytracingsp22_b200 import _ffi
+    hdr = open(os.path.join(ROOT, "include", "rt_b200.h")).read()
+    assert int(re.search(r"#define RT_B200_ABI_VERSION (\d+)", hdr).group(1)) == _ffi.RT_B200_ABI_VERSION
+    assert _ffi.load().rt_abi_version() == _ffi.RT_B200_ABI_VERSION

@@ -21,7 +21,7 @@ def test_library_exports_every_declared_symbol(rtlib):
     for name in sorted(declared):
         assert hasattr(rtlib, name), f"librt_b200.so does not export {name}"
     assert declared == set(_ffi.SIGNATURES), "ctypes table and header disagree"
-    assert rtlib.rt_abi_version() == 2
+    assert rtlib.rt_abi_version() == _ffi.RT_B200_ABI_VERSION == 2
 
 
 def test_struct_layouts_match_the_header():
