@@ -290,6 +290,8 @@ int main(int argc, char** argv) {
   for (int kind = 0; kind < 3; ++kind) {
     Stats s2, s4, s8;
     size_t mismatch = 0;
+    double t_sum = 0.0;           // checksum of the closest hits: must not depend on how the tree was built
+    unsigned long long id_sum = 0;
     for (size_t i = 0; i < n_rays; ++i) {
       Ray r;
       if (kind == 0) {
@@ -322,10 +324,15 @@ int main(int argc, char** argv) {
       }
       float t2, t4, t8;
       int h2 = trace2(M, r, 0.001f, 3.0e38f, t2, s2), h4 = tracew(M, W4, r, 0.001f, 3.0e38f, t4, s4), h8 = tracew(M, W8, r, 0.001f, 3.0e38f, t8, s8);
-      if (h2 >= 0) s2.hits += 1;
+      if (h2 >= 0) {
+        s2.hits += 1;
+        t_sum += t2;
+        id_sum += M.m.tris[(size_t)h2 * RT_TRI_QUADS + 2].u[1];  // original triangle id
+      }
       if ((h2 >= 0) != (h4 >= 0) || (h2 >= 0) != (h8 >= 0) || (h2 >= 0 && (t2 != t4 || t2 != t8))) ++mismatch;
     }
-    std::printf("\nrays %s (%zu, %.1f %% hit, %zu closest-hit mismatches between the trees)\n", names[kind], n_rays, 100.0 * s2.hits / n_rays, mismatch);
+    std::printf("\nrays %s (%zu, %.1f %% hit, %zu closest-hit mismatches between the trees; checksum t %.9g ids %llu)\n", names[kind], n_rays,
+                100.0 * s2.hits / n_rays, mismatch, t_sum, id_sum);
     std::printf("  tree     node fetches  box tests  pushes  leaves  tri tests  max stack   est. instructions\n");
     auto row = [&](const char* nm, const Stats& s, double per_fetch, double per_box) {
       double n = (double)n_rays;
