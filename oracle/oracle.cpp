@@ -1138,6 +1138,25 @@ int orc_sample_hemisphere(const float normal[3], const float ball[3], float out[
   out[0] = d.x; out[1] = d.y; out[2] = d.z;
   return RT_OK;
 }
+// Material::scatter (materials.rs:33-166) for n draws at one surface point: `normal` is the shading normal already
+// turned against the ray (RayHit::new), `frontface` what RayHit::new recorded.  Known-answer probe for the tests.
+int orc_scatter(const rt_material_desc* m, const float normal[3], const float dir[3], int frontface, uint64_t seed, uint32_t n,
+                float* out_dir, float* out_brdf, float* out_pdf) {
+  if (!m || !normal || !dir || !out_dir || !out_brdf || !out_pdf) return RT_ERR_INVALID;
+  Hit h{};
+  h.hitpoint = v3(0, 0, 0);
+  h.normal = v3(normal[0], normal[1], normal[2]);
+  h.frontface = frontface != 0;
+  Ray ray{v3(0, 0, 0), v3(dir[0], dir[1], dir[2])};
+  for (uint32_t i = 0; i < n; ++i) {
+    RngKey key{(uint32_t)seed, (uint32_t)(seed >> 32), i, 0};
+    Scatter s = scatter(*m, h, ray, draw(key, 0, 0));
+    out_dir[3 * i] = s.ray.direction.x; out_dir[3 * i + 1] = s.ray.direction.y; out_dir[3 * i + 2] = s.ray.direction.z;
+    out_brdf[3 * i] = s.brdf.x; out_brdf[3 * i + 1] = s.brdf.y; out_brdf[3 * i + 2] = s.brdf.z;
+    out_pdf[i] = s.pdf;
+  }
+  return RT_OK;
+}
 int orc_texture_sample(const orc_scene* s, int tex, float u, float v, float out[3]) {
   if (!s || tex < 0 || tex >= (int)s->textures.size()) return RT_ERR_INVALID;
   V3 c = tex_sample(s->textures[tex], u, v);

@@ -69,6 +69,7 @@ def load():
         "orc_sample_ball_disk": (C.c_int, [C.c_uint64, C.c_uint32, _F, _F]),
         "orc_philox": (C.c_int, [C.c_uint32] * 6 + [C.POINTER(C.c_uint32)]),
         "orc_sample_hemisphere": (C.c_int, [_F, _F, _F]),
+        "orc_scatter": (C.c_int, [C.POINTER(_ffi.rt_material_desc), _F, _F, C.c_int, C.c_uint64, C.c_uint32, _F, _F, _F]),
         "orc_texture_sample": (C.c_int, [_P, C.c_int, C.c_float, C.c_float, _F]),
         "orc_output_transform": (C.c_int, [_F, C.c_float, _U8]),
         "orc_num_threads": (C.c_int, []),
@@ -226,3 +227,16 @@ def output_transform(mean, gamma):
     out = np.empty(3, np.uint8)
     load().orc_output_transform(_ffi.fptr(_ffi.f3(mean)), gamma, _ffi.u8ptr(out))
     return out
+
+
+def scatter(tag, normal, direction, frontface=True, seed=1, n=1000, albedo=(1, 1, 1), roughness=0.0, metallic=0.0, ior=1.0):
+    """Material::scatter for n draws at one surface point -> (directions, brdf terms, pdfs)."""
+    d = _ffi.rt_material_desc()
+    d.tag = tag
+    d.albedo[:] = [float(v) for v in albedo]
+    d.roughness, d.metallic, d.ior = float(roughness), float(metallic), float(ior)
+    nrm = np.asarray(normal, np.float32); dr = np.asarray(direction, np.float32)
+    out = np.empty((n, 3), np.float32); brdf = np.empty((n, 3), np.float32); pdf = np.empty(n, np.float32)
+    _check(load().orc_scatter(C.byref(d), _ffi.fptr(nrm), _ffi.fptr(dr), int(bool(frontface)), seed, n,
+                              _ffi.fptr(out.reshape(-1)), _ffi.fptr(brdf.reshape(-1)), _ffi.fptr(pdf)))
+    return out, brdf, pdf

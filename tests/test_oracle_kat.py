@@ -345,3 +345,94 @@ def test_orthographic_projection_as_the_reference_writes_it():
     # the sphere of radius 0.25 covers pi r^2 of the 2 x 1 window, wherever the eyepoint is
     frac = (p["obj"] == 0).mean()
     assert abs(frac - math.pi * 0.25 ** 2 / 2.0) < 0.02
+
+
+# ---- Material::scatter (materials.rs:33-166), one surface point, many draws
+N_UP = (0.0, 1.0, 0.0)
+
+
+def _unit(v):
+    v = np.asarray(v, np.float64)
+    return tuple(v / np.linalg.norm(v))
+
+
+def test_lambertian_and_isotropic_scatter():
+    """Lambertian: uniform in the half BALL above the normal (never normalised, Q1), brdf = albedo/pi, pdf = 1/(2 pi), so
+    the mean weight |d.n| * brdf / pdf is 0.75 * albedo (Q2).  Isotropic: the whole ball, brdf = albedo, pdf = 1."""
+    n = _unit((1, 2, -1))
+    d, brdf, pdf = O.scatter(_ffi.RT_MAT_LAMBERTIAN, n, (0, -1, 0), n=100_000, albedo=(0.2, 0.5, 0.8), seed=3)
+    dn = d @ np.asarray(n, np.float32)
+    assert dn.min() >= -1e-6 and np.linalg.norm(d, axis=1).max() <= 1 + 1e-6
+    assert np.allclose(brdf, np.array([0.2, 0.5, 0.8]) / math.pi, rtol=1e-6) and np.allclose(pdf, 1 / (2 * math.pi), rtol=1e-6)
+    assert abs(dn.mean() - 3.0 / 8.0) < 3e-3                       # E|y| of the unit ball
+    weight = (np.clip(np.abs(dn), 0, 1)[:, None] * brdf / pdf[:, None]).mean(axis=0)
+    assert np.allclose(weight, 0.75 * np.array([0.2, 0.5, 0.8]), atol=4e-3)
+    d, brdf, pdf = O.scatter(_ffi.RT_MAT_ISOTROPIC, (0, 0, 0), (0, -1, 0), n=100_000, albedo=(0.3, 0.3, 0.9), seed=4)
+    assert np.abs(d.mean(axis=0)).max() < 5e-3 and abs((d ** 2).sum(axis=1).mean() - 0.6) < 4e-3
+    assert np.allclose(brdf, [0.3, 0.3, 0.9]) and np.all(pdf == 1.0)
+
+
+def test_metal_scatter():
+    """reflect(d, n) + roughness * ball (materials.rs:57-67); the incoming direction is used as it is (length 2 here)."""
+    d_in = np.array([1.0, -1.0, 0.5], np.float32) * 2
+    d, brdf, pdf = O.scatter(_ffi.RT_MAT_METAL, N_UP, d_in, n=50_000, albedo=(0.9, 0.8, 0.7), roughness=0.0)
+    assert np.allclose(d, [2.0, 2.0, 1.0], atol=1e-6) and np.allclose(brdf, [0.9, 0.8, 0.7]) and np.all(pdf == 1.0)
+    d, _, _ = O.scatter(_ffi.RT_MAT_METAL, N_UP, d_in, n=100_000, roughness=0.25, seed=8)
+    off = d - np.array([2.0, 2.0, 1.0], np.float32)
+    assert np.linalg.norm(off, axis=1).max() <= 0.25 + 1e-6 and np.abs(off.mean(axis=0)).max() < 2e-3
+    assert abs(np.linalg.norm(off, axis=1).mean() - 0.25 * 0.75) < 2e-3
+
+
+def test_dielectric_scatter():
+    """materials.rs:80-98 + tracing.rs:58-69: Schlick with r0 = ((ior-1)/(ior+1))^2 on |d.n|, reflection with that
+    probability, Snell refraction otherwise, total internal reflection when eta * sin(theta) > 1 (Q11)."""
+    ior = 1.5
+    r0 = ((ior - 1) / (ior + 1)) ** 2
+    # normal incidence from outside: F = r0 = 0.04; the refracted ray goes straight on
+    d, brdf, pdf = O.scatter(_ffi.RT_MAT_DIELECTRIC, N_UP, (0, -1, 0), frontface=True, n=200_000, ior=ior, seed=5)
+    refl = d[:, 1] > 0
+    assert abs(refl.mean() - r0) < 2e-3
+    assert np.allclose(d[refl], [0, 1, 0], atol=1e-6) and np.allclose(d[~refl], [0, -1, 0], atol=1e-6)
+    assert np.all(brdf == 1.0) and np.all(pdf == 1.0)
+    # 60 degrees from outside: F = r0 + (1-r0) * (1 - cos)^5, refraction obeys sin(t) = sin(i) / ior
+    th = math.radians(60.0)
+    d_in = (math.sin(th), -math.cos(th), 0.0)
+    fres = r0 + (1 - r0) * (1 - math.cos(th)) ** 5
+    d, _, _ = O.scatter(_ffi.RT_MAT_DIELECTRIC, N_UP, d_in, frontface=True, n=200_000, ior=ior, seed=6)
+    refl = d[:, 1] > 0
+    assert abs(refl.mean() - fres) < 3e-3
+    assert np.allclose(d[refl], [math.sin(th), math.cos(th), 0], atol=1e-6)
+    sin_t = math.sin(th) / ior
+    assert np.allclose(d[~refl], [sin_t, -math.sqrt(1 - sin_t ** 2), 0], atol=1e-6)
+    # from inside (the stored normal faces the ray, frontface = false, eta = ior): beyond asin(1/1.5) = 41.8 deg everything reflects
+    for deg, tir in ((30.0, False), (45.0, True), (80.0, True)):
+        th = math.radians(deg)
+        d, _, _ = O.scatter(_ffi.RT_MAT_DIELECTRIC, N_UP, (math.sin(th), -math.cos(th), 0.0), frontface=False, n=20_000, ior=ior, seed=7)
+        refl = d[:, 1] > 0
+        assert refl.all() if tir else (0.0 < refl.mean() < 0.2)
+        if not tir:
+            sin_t = math.sin(th) * ior
+            assert np.allclose(d[~refl], [sin_t, -math.sqrt(1 - sin_t ** 2), 0], atol=1e-5)
+
+
+def test_parameterized_scatter():
+    """materials.rs:114-145: k_s = F(ior 1.5) * (1 - roughness), k_d = (1 - k_s)(1 - metallic); with probability k_d the
+    Lambertian lobe (albedo/pi, 1/(2 pi)), otherwise the metal lobe with brdf lerp(white, albedo, metallic), pdf 1."""
+    albedo = np.array([0.01, 0.02, 0.5])
+    th = math.radians(50.0)
+    d_in = (math.sin(th), -math.cos(th), 0.0)
+    r0 = 0.04
+    fres = r0 + (1 - r0) * (1 - math.cos(th)) ** 5
+    for rough, metallic in ((0.0, 0.0), (0.25, 0.5), (1.0, 0.0), (0.5, 1.0)):
+        d, brdf, pdf = O.scatter(_ffi.RT_MAT_PARAMETERIZED, N_UP, d_in, n=200_000, albedo=albedo, roughness=rough, metallic=metallic,
+                                 seed=int(10 + 10 * rough + metallic * 100))
+        k_d = (1 - fres * (1 - rough)) * (1 - metallic)
+        diffuse = pdf < 0.5
+        assert abs(diffuse.mean() - k_d) < 3e-3, (rough, metallic)
+        if diffuse.any():
+            assert np.allclose(brdf[diffuse], albedo / math.pi, rtol=1e-5) and np.allclose(pdf[diffuse], 1 / (2 * math.pi), rtol=1e-6)
+            assert d[diffuse][:, 1].min() >= -1e-6
+        if (~diffuse).any():
+            assert np.allclose(brdf[~diffuse], (1 - metallic) * np.ones(3) + metallic * albedo, atol=1e-6)
+            off = d[~diffuse] - np.array([math.sin(th), math.cos(th), 0.0], np.float32)
+            assert np.linalg.norm(off, axis=1).max() <= rough + 1e-5
