@@ -436,3 +436,43 @@ def test_parameterized_scatter():
             assert np.allclose(brdf[~diffuse], (1 - metallic) * np.ones(3) + metallic * albedo, atol=1e-6)
             off = d[~diffuse] - np.array([math.sin(th), math.cos(th), 0.0], np.float32)
             assert np.linalg.norm(off, axis=1).max() <= rough + 1e-5
+
+
+def test_defocus_rays_meet_on_the_focus_sphere():
+    """Camera::generate_rays (tracing.rs:176-203): the lens sample is uniform on a disk of lens_radius around the eye, and
+    every ray of a pixel sample passes through normalize(pixel centre) * focus_dist - a focus SPHERE, not a plane (Q8)."""
+    kw = dict(eyepoint=(1.0, 2.0, 3.0), screen_width=24, screen_height=16, aa_sample_count=16, focal_length=0.8, focus_dist=4.0)
+    sc = rt.Scene(camera=rt.Camera(**kw), objects=[rt.Sphere((0, 0, -50), 1.0, rt.Lambertian())])
+    o = O.lower_to_oracle(sc)
+    eye = np.array(kw["eyepoint"], np.float32)
+    origins = []
+    for sample in (0, 5, 11):
+        pin = o.trace_primary(rt.Camera(lens_radius=0.0, **kw).to_c(), 21, sample)["ray"]
+        lens = o.trace_primary(rt.Camera(lens_radius=0.3, **kw).to_c(), 21, sample)["ray"]
+        assert np.allclose(pin[:, :3], eye) and np.allclose(np.linalg.norm(pin[:, 3:], axis=1), 1.0, atol=1e-6)
+        focus = pin[:, :3] + pin[:, 3:] * 4.0                       # on the sphere of radius focus_dist around the eye
+        lo, ld = lens[:, :3], lens[:, 3:]
+        assert np.allclose(np.linalg.norm(ld, axis=1), 1.0, atol=1e-6)
+        miss = np.linalg.norm(np.cross(focus - lo, ld), axis=1)     # distance from the focus point to the lens ray
+        assert miss.max() < 2e-5
+        assert np.allclose(lo[:, 2], eye[2], atol=1e-6)             # the lens lies in the camera's xy plane
+        origins.append(lo - eye)
+    r = np.linalg.norm(np.concatenate(origins), axis=1)
+    assert r.max() <= 0.3 + 1e-6 and abs((r ** 2).mean() - 0.3 ** 2 / 2) < 3e-3   # uniform on the disk
+
+
+def test_triangle_determinant_epsilon_is_in_parametric_units():
+    """Triangle::intersect_ray (geometry.rs:433-438): |det| < 1e-4 is a miss, with det = e1 . (d x e2) for the direction AS
+    GIVEN - so a small triangle that a unit-length ray cannot hit is hit by the same ray with a longer direction (Q1, Q5)."""
+    tri = rt.Triangle((0, 0, 0), (0.009, 0, 0), (0, 0.009, 0), rt.Lambertian())
+    o = O.lower_to_oracle(rt.Scene(camera=rt.Camera(), objects=[tri]))
+    ray = np.array([[0.002, 0.002, 1.0, 0, 0, -1.0]], np.float32)
+    assert o.intersect_rays(ray, 0.001, 100.0)["obj"][0] == -1       # det = 8.1e-5
+    ray2 = ray.copy()
+    ray2[:, 3:] *= 2.0                                               # det = 1.62e-4, t halves
+    res = o.intersect_rays(ray2, 0.001, 100.0)
+    assert res["obj"][0] == 0 and abs(res["t"][0] - 0.5) < 1e-6
+    # both faces are hit (no culling), the reported normal faces the ray
+    back = np.array([[0.002, 0.002, -1.0, 0, 0, 2.0]], np.float32)
+    res = o.intersect_rays(back, 0.001, 100.0)
+    assert res["obj"][0] == 0 and res["normal"][0, 2] < 0 and res["frontface"][0] == 0
