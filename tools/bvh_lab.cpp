@@ -255,6 +255,7 @@ int main(int argc, char** argv) {
   M.m.nrm.assign(om.nrm, om.nrm + 3 * (size_t)om.nverts);
   M.m.uv.assign(om.uv, om.uv + 2 * (size_t)om.nverts);
   M.m.idx.assign(om.idx, om.idx + 3 * (size_t)om.ntris);
+  std::free(om.pos); std::free(om.nrm); std::free(om.uv); std::free(om.idx);
   rt::build_mesh(M.m);
   const size_t ntri = M.m.tris.size() / RT_TRI_QUADS;
   std::printf("%s: %u triangles, %zu reachable, %zu binary nodes, depth %u\n", argv[1], om.ntris, ntri, M.m.nodes.size() / 2, M.m.depth);
