@@ -1,0 +1,33 @@
+// rt_config.cuh — compile-time knobs of the kernels (each one was measured, see profiles/r1_notes.md)
+#ifndef RT_CONFIG_CUH
+#define RT_CONFIG_CUH
+
+#ifndef RT_BLOCK
+#define RT_BLOCK 128
+#endif
+#define RT_WARPS (RT_BLOCK / 32)
+#ifndef RT_SMEM_STACK
+#define RT_SMEM_STACK 16   // traversal-stack entries per thread kept in shared memory
+#endif
+#define RT_LOCAL_STACK 48  // overflow entries (local memory; host checks depth <= 62)
+// RT_STREAM_HINTS: ray queue / hit record traffic uses the streaming (evict-first) cache operators so that it does
+// not push BVH nodes, triangles and texels out of L1/L2.  (Tried and dropped, profiles/r1_notes.md B2, B6: stack
+// entries that carry their entry distance, and prefetching the children of the pushed child.)
+#ifndef RT_STREAM_HINTS
+#define RT_STREAM_HINTS 1
+#endif
+#if RT_STREAM_HINTS
+#define RT_LDS(p) __ldcs(p)
+#define RT_STS(p, v) __stcs(p, v)
+#else
+#define RT_LDS(p) (*(p))
+#define RT_STS(p, v) (*(p) = (v))
+#endif
+#ifndef RT_OCTANT_SORT
+#define RT_OCTANT_SORT 1
+#endif
+#ifndef RT_EXTEND_MIN_BLOCKS
+#define RT_EXTEND_MIN_BLOCKS 8  // 64 registers per thread -> 32 resident warps per SM
+#endif
+
+#endif
