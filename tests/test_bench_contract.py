@@ -38,7 +38,7 @@ def test_product_code_never_touches_the_oracle():
     for base in ("cs397raytracingsp22_b200", "include", "examples"):
         for dirpath, _, files in os.walk(os.path.join(ROOT, base)):
             for f in files:
-                if not f.endswith((".py", ".cu", ".cpp", ".h", ".hpp")):
+                if not f.endswith((".py", ".cu", ".cuh", ".cpp", ".h", ".hpp")):
                     continue
                 text = open(os.path.join(dirpath, f), errors="replace").read()
                 if re.search(r"oracle_ffi|liboracle|orc_[a-z_]+\(|[\"'/]oracle/", text):
