@@ -18,11 +18,15 @@ _LIB = None
 RT_OK = 0
 RT_ERR_INVALID, RT_ERR_UNSUPPORTED, RT_ERR_CUDA, RT_ERR_IO, RT_ERR_NOT_COMMITTED = -1, -2, -3, -4, -5
 RT_MAT_LAMBERTIAN, RT_MAT_METAL, RT_MAT_DIELECTRIC, RT_MAT_PARAMETERIZED, RT_MAT_ISOTROPIC = range(5)
-RT_B200_ABI_VERSION = 2  # include/rt_b200.h
+RT_B200_ABI_VERSION = 3  # include/rt_b200.h
 RT_PROJ_ORTHOGRAPHIC, RT_PROJ_PERSPECTIVE = 0, 1
 RT_SHADE_PHONG, RT_SHADE_PATHTRACE = 0, 1
 RT_SHARD_ALL, RT_SHARD_SAMPLES, RT_SHARD_TILES = 0, 1, 2
 RT_OPT_COUNTERS, RT_OPT_NO_EVENTS = 1, 2
+RT_ENGINE_AUTO, RT_ENGINE_WAVEFRONT, RT_ENGINE_MEGAKERNEL = 0, 1, 2
+RT_RAYSORT_AUTO, RT_RAYSORT_OFF, RT_RAYSORT_ON = 0, 1, 2
+RT_ORDER_AUTO, RT_ORDER_PIXEL_MAJOR, RT_ORDER_SAMPLE_MAJOR, RT_ORDER_GROUPED = 0, 1, 2, 3
+ENGINES = {"auto": RT_ENGINE_AUTO, "wavefront": RT_ENGINE_WAVEFRONT, "megakernel": RT_ENGINE_MEGAKERNEL}
 
 
 class RtError(RuntimeError):
@@ -48,7 +52,9 @@ class rt_render_opts(C.Structure):
     _fields_ = [("seed", C.c_uint64), ("shard_mode", C.c_uint32), ("shard_rank", C.c_uint32),
                 ("shard_count", C.c_uint32), ("tile_size", C.c_uint32), ("sample_begin", C.c_uint32),
                 ("sample_end", C.c_uint32), ("wavefront", C.c_uint32), ("flags", C.c_uint32),
-                ("point_light_pos", C.c_float * 3), ("ambient", C.c_float * 3)]
+                ("point_light_pos", C.c_float * 3), ("ambient", C.c_float * 3),
+                ("engine", C.c_uint32), ("ray_sort", C.c_uint32), ("work_order", C.c_uint32),
+                ("blocks_per_sm", C.c_uint32), ("reserved", C.c_uint32 * 4)]
 
 
 class rt_stats(C.Structure):

@@ -10,6 +10,8 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <new>
+#include <stdexcept>
 #include <string>
 #include <vector>
 
@@ -34,17 +36,6 @@ struct DevBuf {
 };
 }  // namespace
 
-#define RT_MAX_LANES 4
-#ifndef RT_DEFAULT_LANES
-#define RT_DEFAULT_LANES 1
-#endif
-#ifndef RT_DEFAULT_SAMPLE_MAJOR
-#define RT_DEFAULT_SAMPLE_MAJOR 0
-#endif
-#ifndef RT_DEFAULT_RAY_SORT
-#define RT_DEFAULT_RAY_SORT 1
-#endif
-
 struct rt_scene {
   std::vector<rt::HostTexture> textures;
   std::vector<rt_material_desc> materials;
@@ -60,26 +51,24 @@ struct rt_scene {
   DevBuf d_nodes, d_tris, d_shade, d_objects, d_mats, d_textures, d_texels, d_planes, d_guards, d_guard_list;
   rt_dev_scene dev{};
 
-  // wavefront state: one or more independent "lanes" (ray queues + control block + stream).  Several lanes let
-  // the tail of one lane's k_trace and its bandwidth-bound k_shade overlap the other lane's traversal.
-  struct Lane {
+  // wavefront engine state: ray queues, hit records, shade queues, sort buffers, control block
+  struct Wavefront {
     uint32_t capacity = 0;
     rt::rt_paths paths[2] = {};
     rt::rt_hits hits = {};
     uint32_t* queues = nullptr;
     rt::rt_sortbuf sort = {};
-    rt_ctrl* ctrl = nullptr;
+    rt_ctrl* ctrl = nullptr;     // also the control block of the megakernel engine
     rt_ctrl* h_ctrl = nullptr;   // pinned
     uint32_t* h_done = nullptr;  // pinned poll slots
     cudaEvent_t poll_ev[2] = {nullptr, nullptr};
-    cudaEvent_t end_ev = nullptr;
     std::vector<cudaEvent_t> events;
-    cudaStream_t stream = nullptr;
   };
-  Lane lanes[RT_MAX_LANES];
+  Wavefront wf;
   cudaStream_t own_stream = nullptr;
-  cudaEvent_t begin_ev = nullptr;
-  uint32_t persistent_blocks = 148 * 8;  // k_trace grid: SM count x resident blocks per SM
+  uint32_t sm_count = 148;
+  uint32_t trace_blocks_per_sm = 8;  // resident blocks per SM of the persistent kernels (occupancy query)
+  uint32_t path_blocks_per_sm = 6;
   // scratch for host-buffer entry points
   DevBuf d_accum, d_linear, d_rgb8, d_dbg;
   DevBuf d_tree[3];  // ray pool of the depth-first walk (path_samples > 1)
@@ -120,7 +109,8 @@ int upload(DevBuf& b, const void* src, size_t bytes, cudaStream_t st) {
   return RT_OK;
 }
 
-void free_lane(rt_scene::Lane& L) {
+void free_wavefront(rt_scene* s) {
+  rt_scene::Wavefront& L = s->wf;
   for (int k = 0; k < 2; ++k) {
     if (L.paths[k].A) cudaFree(L.paths[k].A);
     if (L.paths[k].B) cudaFree(L.paths[k].B);
@@ -137,37 +127,35 @@ void free_lane(rt_scene::Lane& L) {
   L.sort.keys = L.sort.order = nullptr;
   L.capacity = 0;
 }
-void free_wavefront(rt_scene* s) {
-  for (auto& L : s->lanes) free_lane(L);
-}
 
+// stream, control block, poll slots: what both engines need
 int ensure_runtime(rt_scene* s) {
   if (s->own_stream) return RT_OK;
   CUDA_TRY(cudaStreamCreateWithFlags(&s->own_stream, cudaStreamNonBlocking));
-  CUDA_TRY(cudaEventCreateWithFlags(&s->begin_ev, cudaEventDisableTiming));
   int sms = 0;
   CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, s->device));
-  int per_sm = rt::trace_blocks_per_sm();
-  if (const char* e = std::getenv("RT_TRACE_BLOCKS")) per_sm = std::max(1, std::min(per_sm, std::atoi(e)));
-  s->persistent_blocks = (uint32_t)(sms * per_sm);
+  s->sm_count = (uint32_t)std::max(1, sms);
+  s->trace_blocks_per_sm = (uint32_t)rt::trace_blocks_per_sm();
+  s->path_blocks_per_sm = (uint32_t)rt::path_blocks_per_sm();
+  rt_scene::Wavefront& L = s->wf;
+  CUDA_TRY(cudaMalloc((void**)&L.ctrl, sizeof(rt_ctrl)));
+  CUDA_TRY(cudaMallocHost((void**)&L.h_ctrl, sizeof(rt_ctrl)));
+  CUDA_TRY(cudaMallocHost((void**)&L.h_done, 2 * sizeof(uint32_t)));
+  CUDA_TRY(cudaEventCreateWithFlags(&L.poll_ev[0], cudaEventDisableTiming));
+  CUDA_TRY(cudaEventCreateWithFlags(&L.poll_ev[1], cudaEventDisableTiming));
   return RT_OK;
 }
+uint32_t persistent_grid(const rt_scene* s, uint32_t per_sm_default, uint32_t requested) {
+  uint32_t per_sm = requested ? std::min(requested, per_sm_default) : per_sm_default;
+  return s->sm_count * std::max(1u, per_sm);
+}
 
-int ensure_lane(rt_scene* s, int li, uint32_t capacity) {
+int ensure_wavefront(rt_scene* s, uint32_t capacity) {
   int rc = ensure_runtime(s);
   if (rc != RT_OK) return rc;
-  rt_scene::Lane& L = s->lanes[li];
-  if (!L.ctrl) {
-    CUDA_TRY(cudaMalloc((void**)&L.ctrl, sizeof(rt_ctrl)));
-    CUDA_TRY(cudaMallocHost((void**)&L.h_ctrl, sizeof(rt_ctrl)));
-    CUDA_TRY(cudaMallocHost((void**)&L.h_done, 2 * sizeof(uint32_t)));
-    CUDA_TRY(cudaEventCreateWithFlags(&L.poll_ev[0], cudaEventDisableTiming));
-    CUDA_TRY(cudaEventCreateWithFlags(&L.poll_ev[1], cudaEventDisableTiming));
-    CUDA_TRY(cudaEventCreateWithFlags(&L.end_ev, cudaEventDisableTiming));
-    CUDA_TRY(cudaStreamCreateWithFlags(&L.stream, cudaStreamNonBlocking));
-  }
+  rt_scene::Wavefront& L = s->wf;
   if (L.capacity >= capacity && L.queues) return RT_OK;
-  free_lane(L);
+  free_wavefront(s);
   size_t n = capacity;
   for (int k = 0; k < 2; ++k) {
     CUDA_TRY(cudaMalloc((void**)&L.paths[k].A, n * 16));
@@ -188,8 +176,6 @@ int ensure_lane(rt_scene* s, int li, uint32_t capacity) {
   L.capacity = capacity;
   return RT_OK;
 }
-// kept for the entry points that only need the runtime objects / lane 0
-int ensure_wavefront(rt_scene* s, uint32_t capacity) { return ensure_lane(s, 0, capacity); }
 
 int check_camera(const rt_camera* cam) {
   if (!cam) return fail(RT_ERR_INVALID, "camera is NULL");
@@ -302,8 +288,13 @@ int plan_shard(const rt_camera& cam, const rt_render_opts& o, rt_frame& fr, unsi
   // and sample-range shards.  2: the same warps, but consecutive warps walk the shard's pixels - a tile shard at high
   // spp otherwise keeps the whole wavefront inside half a tile, which piles the ray-sort keys into a few bins (C5 on
   // 1/8 of the tiles: 1399 -> 1645 Msamples/s).  1: sample-major (a warp = 32 neighbouring pixels), slower everywhere.
-  fr.sample_major = o.shard_mode == RT_SHARD_TILES ? 2u : (uint32_t)RT_DEFAULT_SAMPLE_MAJOR;
-  if (const char* e = std::getenv("RT_SAMPLE_MAJOR")) fr.sample_major = (uint32_t)std::max(0, std::min(2, std::atoi(e)));
+  switch (o.work_order) {
+    case RT_ORDER_AUTO: fr.sample_major = o.shard_mode == RT_SHARD_TILES ? 2u : 0u; break;
+    case RT_ORDER_PIXEL_MAJOR: fr.sample_major = 0u; break;
+    case RT_ORDER_SAMPLE_MAJOR: fr.sample_major = 1u; break;
+    case RT_ORDER_GROUPED: fr.sample_major = 2u; break;
+    default: return fail(RT_ERR_INVALID, "unknown work_order");
+  }
   if (fr.sample_major == 2u && (fr.sample_count % 32u) != 0u) fr.sample_major = 0;  // needs whole groups of 32 samples
   total = fr.sample_count ? npix * fr.sample_count : 0;
   if (fr.sample_count == 0) fr.sample_count = 1;  // never divide by zero on the device
@@ -329,181 +320,172 @@ int set_device(rt_scene* s) {
   return RT_OK;
 }
 
+// what one engine run leaves in rt_stats
+void stats_from_ctrl(const rt_ctrl& c, rt_stats* stats) {
+  stats->samples += c.n_samples - c.counters[7];
+  stats->rays += c.n_rays_total - c.counters[7] - c.counters[11];  // [11]: Phong shadow slots of missed camera rays
+  stats->nodes_visited += c.counters[0];
+  stats->tris_tested += c.counters[1];
+  stats->instances_entered += c.counters[2];
+  stats->prims_tested += c.counters[3];
+  stats->mesh_hits += c.counters[4];
+  stats->texel_taps += c.counters[5] + c.counters[8];
+  stats->extend_texel_taps += c.counters[8];
+  stats->material_fetches += c.counters[6];
+  stats->warp_node_slots += c.counters[9];
+  stats->tlas_nodes_visited += c.counters[10];
+}
+
 // The wavefront loop.  Launches are asynchronous; the device decides how many rays each iteration has.  The host
-// only peeks at a `done` flag every few iterations, two polls deep, so the streams never drain.  With several lanes
-// the frame's work indices are cut into contiguous ranges, one per lane, and the lanes' iterations are enqueued
-// round-robin on their own streams.
+// only peeks at a `done` flag every few iterations, two polls deep, so the stream never drains.
 int run_wavefront(rt_scene* s, const rt_frame& fr_in, unsigned long long total, long long* d_accum, bool count,
-                  bool use_events, cudaStream_t user_st, int nlanes, rt_stats* stats) {
+                  bool use_events, cudaStream_t st, uint32_t blocks_per_sm, rt_stats* stats) {
   int rc;
-  nlanes = std::max(1, std::min(nlanes, RT_MAX_LANES));
-  if (total < (unsigned long long)nlanes * 65536ull) nlanes = 1;  // tiny jobs: one lane
   rt_frame fr = fr_in;
-  if (fr.phong) {  // camera ray + shadow ray pairs: slot i of the shadow pass belongs to slot i of the camera pass
-    nlanes = 1;
-    fr.sort_enabled = 0;
-  }
-  fr.capacity = std::max<uint32_t>(128u, (fr.capacity / (uint32_t)nlanes + 127u) / 128u * 128u);
-  for (int li = 0; li < nlanes; ++li)
-    if ((rc = ensure_lane(s, li, fr.capacity)) != RT_OK) return rc;
+  if (fr.phong) fr.sort_enabled = 0;  // camera ray + shadow ray pairs: slot i of the shadow pass belongs to slot i of the camera pass
+  fr.capacity = std::max<uint32_t>(128u, (fr.capacity + 127u) / 128u * 128u);
+  if ((rc = ensure_wavefront(s, fr.capacity)) != RT_OK) return rc;
+  rt_scene::Wavefront& L = s->wf;
+  const uint32_t grid = persistent_grid(s, s->trace_blocks_per_sm, blocks_per_sm);
   const int kChunk = 8;
   const size_t kMaxTimedIters = 1u << 14;
-  struct LaneRun {
-    size_t ev_used = 0, ev_iter_base = 0, timed_iters = 0;
-    uint64_t launches = 0, ext = 0, shd = 0;
-    unsigned long long it = 0;
-    int chunk = 0;
-    bool done = false;
-    cudaStream_t st = nullptr;
-  } run[RT_MAX_LANES];
-  auto next_event = [&](int li, cudaEvent_t& ev) -> int {
-    rt_scene::Lane& L = s->lanes[li];
-    if (run[li].ev_used == L.events.size()) {
+  size_t ev_used = 0, timed_iters = 0;
+  uint64_t launches = 0, ext = 0, shd = 0;
+  unsigned long long it = 0;
+  auto next_event = [&](cudaEvent_t& ev) -> int {
+    if (ev_used == L.events.size()) {
       cudaEvent_t e;
       CUDA_TRY(cudaEventCreate(&e));
       L.events.push_back(e);
     }
-    ev = L.events[run[li].ev_used++];
+    ev = L.events[ev_used++];
     return RT_OK;
   };
-  // frame begin / end are timed on the caller's stream; lane streams fork from it and join it again
   cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
-  if ((rc = next_event(0, ev_begin)) != RT_OK || (rc = next_event(0, ev_end)) != RT_OK) return rc;
-  CUDA_TRY(cudaEventRecord(ev_begin, user_st));
-  if (nlanes > 1) CUDA_TRY(cudaEventRecord(s->begin_ev, user_st));
-  for (int li = 0; li < nlanes; ++li) {
-    rt_scene::Lane& L = s->lanes[li];
-    run[li].st = nlanes == 1 ? user_st : L.stream;
-    if (nlanes > 1) CUDA_TRY(cudaStreamWaitEvent(run[li].st, s->begin_ev, 0));
-    unsigned long long b = total * (unsigned long long)li / (unsigned long long)nlanes;
-    unsigned long long e = total * (unsigned long long)(li + 1) / (unsigned long long)nlanes;
-    rt::launch_init(L.ctrl, b, e, run[li].st);
-    run[li].launches = 1;
-    run[li].ev_iter_base = run[li].ev_used;
-    L.h_done[0] = L.h_done[1] = 0;
-  }
-  int live = nlanes;
-  while (live > 0) {
-    for (int k = 0; k < kChunk; ++k)
-      for (int li = 0; li < nlanes; ++li) {
-        LaneRun& R = run[li];
-        if (R.done) continue;
-        rt_scene::Lane& L = s->lanes[li];
-        cudaStream_t st = R.st;
-        int cur = (int)(R.it & 1), nxt = cur ^ 1;
+  if ((rc = next_event(ev_begin)) != RT_OK || (rc = next_event(ev_end)) != RT_OK) return rc;
+  const size_t ev_iter_base = ev_used;
+  CUDA_TRY(cudaEventRecord(ev_begin, st));
+  rt::launch_init(L.ctrl, 0ull, total, st);
+  launches = 1;
+  L.h_done[0] = L.h_done[1] = 0;
+  bool done = false;
+  for (int chunk = 0; !done; ++chunk) {
+    for (int k = 0; k < kChunk; ++k) {
+      int cur = (int)(it & 1), nxt = cur ^ 1;
+      rt::launch_advance(L.ctrl, fr.capacity, st);
+      bool timed = use_events && timed_iters < kMaxTimedIters;
+      cudaEvent_t e0 = nullptr, e1 = nullptr, e2 = nullptr;
+      rt::launch_raygen(fr, L.ctrl, L.paths[cur], st);
+      if (timed) {
+        if ((rc = next_event(e0)) != RT_OK || (rc = next_event(e1)) != RT_OK || (rc = next_event(e2)) != RT_OK) return rc;
+        CUDA_TRY(cudaEventRecord(e0, st));
+      }
+      rt::launch_trace(s->dev, fr, L.ctrl, L.paths[cur], L.hits, L.sort, count, grid, st);  // dominant kernel
+      if (timed) CUDA_TRY(cudaEventRecord(e1, st));
+      if (fr.phong) {
+        // ShadingMode::Phong (tracing.rs:277-297).  k_phong_primary leaves n_next = n_rays, so the second
+        // k_advance admits no new work (a batch is either full or the last one) and the shadow rays keep their slots.
+        rt::launch_phong_primary(s->dev, fr, L.ctrl, L.paths[cur], L.paths[nxt], L.hits, st);
         rt::launch_advance(L.ctrl, fr.capacity, st);
-        bool timed = use_events && R.timed_iters < kMaxTimedIters;
-        cudaEvent_t e0 = nullptr, e1 = nullptr, e2 = nullptr;
-        rt::launch_raygen(fr, L.ctrl, L.paths[cur], st);
-        if (timed) {
-          if ((rc = next_event(li, e0)) != RT_OK || (rc = next_event(li, e1)) != RT_OK || (rc = next_event(li, e2)) != RT_OK) return rc;
-          CUDA_TRY(cudaEventRecord(e0, st));
-        }
-        rt::launch_trace(s->dev, fr, L.ctrl, L.paths[cur], L.hits, L.sort, count, s->persistent_blocks, st);  // dominant kernel
-        if (timed) CUDA_TRY(cudaEventRecord(e1, st));
-        if (fr.phong) {
-          // ShadingMode::Phong (tracing.rs:277-297).  k_phong_primary leaves n_next = n_rays, so the second
-          // k_advance admits no new work (a batch is either full or the last one) and the shadow rays keep their slots.
-          rt::launch_phong_primary(s->dev, fr, L.ctrl, L.paths[cur], L.paths[nxt], L.hits, st);
-          rt::launch_advance(L.ctrl, fr.capacity, st);
-          rt_frame fs = fr;
-          fs.ray_tmax_from_c = 1;
-          rt::launch_trace(s->dev, fs, L.ctrl, L.paths[nxt], L.hits, L.sort, count, s->persistent_blocks, st);
-          rt::launch_phong_shadow(s->dev, fr, L.ctrl, L.paths[nxt], L.hits, d_accum, st);
-          if (timed) {
-            CUDA_TRY(cudaEventRecord(e2, st));
-            ++R.timed_iters;
-          }
-          R.launches += 7; R.ext += 2; R.shd += 2; R.it += 2;
-          continue;
-        }
-        rt::launch_sort(s->dev, fr, L.ctrl, L.hits, L.queues, st);
-        rt::launch_shade(s->dev, fr, L.ctrl, L.paths[cur], L.paths[nxt], L.hits, L.queues, d_accum, L.sort, count, st);
-        rt::launch_raysort(fr, L.ctrl, L.sort, st);
+        rt_frame fs = fr;
+        fs.ray_tmax_from_c = 1;
+        rt::launch_trace(s->dev, fs, L.ctrl, L.paths[nxt], L.hits, L.sort, count, grid, st);
+        rt::launch_phong_shadow(s->dev, fr, L.ctrl, L.paths[nxt], L.hits, d_accum, st);
         if (timed) {
           CUDA_TRY(cudaEventRecord(e2, st));
-          ++R.timed_iters;
+          ++timed_iters;
         }
-        R.launches += fr.sort_enabled ? 7 : 5; ++R.ext; ++R.shd; ++R.it;
+        launches += 7; ext += 2; shd += 2; it += 2;
+        continue;
       }
-    // poll each lane: copy the done flag written by k_advance, two chunks deep
-    for (int li = 0; li < nlanes; ++li) {
-      LaneRun& R = run[li];
-      if (R.done) continue;
-      rt_scene::Lane& L = s->lanes[li];
-      int slot = R.chunk & 1;
-      if (R.chunk >= 2) {
-        CUDA_TRY(cudaEventSynchronize(L.poll_ev[slot]));
-        if (L.h_done[slot]) {
-          R.done = true;
-          --live;
-        }
+      rt::launch_sort(s->dev, fr, L.ctrl, L.hits, L.queues, st);
+      rt::launch_shade(s->dev, fr, L.ctrl, L.paths[cur], L.paths[nxt], L.hits, L.queues, d_accum, L.sort, count, st);
+      rt::launch_raysort(fr, L.ctrl, L.sort, st);
+      if (timed) {
+        CUDA_TRY(cudaEventRecord(e2, st));
+        ++timed_iters;
       }
-      if (!R.done) {
-        CUDA_TRY(cudaMemcpyAsync(&L.h_done[slot], &L.ctrl->done, sizeof(uint32_t), cudaMemcpyDeviceToHost, R.st));
-        CUDA_TRY(cudaEventRecord(L.poll_ev[slot], R.st));
-      }
-      ++R.chunk;
+      launches += fr.sort_enabled ? 7 : 5; ++ext; ++shd; ++it;
+    }
+    // poll: copy the done flag written by k_advance, two chunks deep
+    int slot = chunk & 1;
+    if (chunk >= 2) {
+      CUDA_TRY(cudaEventSynchronize(L.poll_ev[slot]));
+      if (L.h_done[slot]) done = true;
+    }
+    if (!done) {
+      CUDA_TRY(cudaMemcpyAsync(&L.h_done[slot], &L.ctrl->done, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+      CUDA_TRY(cudaEventRecord(L.poll_ev[slot], st));
     }
   }
-  for (int li = 0; li < nlanes; ++li) {
-    rt_scene::Lane& L = s->lanes[li];
-    CUDA_TRY(cudaMemcpyAsync(L.h_ctrl, L.ctrl, sizeof(rt_ctrl), cudaMemcpyDeviceToHost, run[li].st));
-    if (nlanes > 1) {
-      CUDA_TRY(cudaEventRecord(L.end_ev, run[li].st));
-      CUDA_TRY(cudaStreamWaitEvent(user_st, L.end_ev, 0));
-    }
-  }
-  CUDA_TRY(cudaEventRecord(ev_end, user_st));
-  CUDA_TRY(cudaStreamSynchronize(user_st));
+  CUDA_TRY(cudaMemcpyAsync(L.h_ctrl, L.ctrl, sizeof(rt_ctrl), cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaEventRecord(ev_end, st));
+  CUDA_TRY(cudaStreamSynchronize(st));
   CUDA_TRY(cudaGetLastError());
-  for (int li = 0; li < nlanes; ++li) {
-    const rt_ctrl& c = *s->lanes[li].h_ctrl;
-    if (!c.done && c.cursor != c.total) return fail(RT_ERR_CUDA, "wavefront loop ended before all work was issued");
-  }
+  const rt_ctrl& c = *L.h_ctrl;
+  if (!c.done && c.cursor != c.total) return fail(RT_ERR_CUDA, "wavefront loop ended before all work was issued");
   if (stats) {
     float ms = 0.0f;
     cudaEventElapsedTime(&ms, ev_begin, ev_end);
     stats->ms_total += ms;
-    for (int li = 0; li < nlanes; ++li) {
-      const rt_scene::Lane& L = s->lanes[li];
-      const LaneRun& R = run[li];
-      const rt_ctrl& c = *L.h_ctrl;
-      stats->samples += c.n_samples - c.counters[7];
-      stats->rays += c.n_rays_total - c.counters[7] - c.counters[11];  // [11]: Phong shadow slots of missed camera rays
-      stats->iterations += c.iterations;
-      stats->kernel_launches += R.launches;
-      // report the launches that did work, not the no-op tail queued behind the `done` poll
-      stats->extend_launches += std::min<uint64_t>(R.ext, c.iterations);
-      stats->shade_launches += std::min<uint64_t>(R.shd, c.iterations);
-      stats->nodes_visited += c.counters[0];
-      stats->tris_tested += c.counters[1];
-      stats->instances_entered += c.counters[2];
-      stats->prims_tested += c.counters[3];
-      stats->mesh_hits += c.counters[4];
-      stats->texel_taps += c.counters[5] + c.counters[8];
-      stats->extend_texel_taps += c.counters[8];
-      stats->material_fetches += c.counters[6];
-      stats->warp_node_slots += c.counters[9];
-      stats->tlas_nodes_visited += c.counters[10];
-      // only iterations that actually had rays count as launches of the dominant kernel
-      double me = 0.0, msd = 0.0;
-      size_t live_it = std::min<size_t>(R.timed_iters, c.iterations);
-      for (size_t i = 0; i < live_it; ++i) {
-        float a = 0.0f, b = 0.0f;
-        cudaEventElapsedTime(&a, L.events[R.ev_iter_base + 3 * i], L.events[R.ev_iter_base + 3 * i + 1]);
-        cudaEventElapsedTime(&b, L.events[R.ev_iter_base + 3 * i + 1], L.events[R.ev_iter_base + 3 * i + 2]);
-        me += a;
-        msd += b;
-      }
-      if (live_it && live_it < c.iterations) {  // more iterations than event slots: scale up
-        double f = (double)c.iterations / (double)live_it;
-        me *= f;
-        msd *= f;
-      }
-      stats->ms_extend += me;
-      stats->ms_shade += msd;
+    stats_from_ctrl(c, stats);
+    stats->iterations += c.iterations;
+    stats->kernel_launches += launches;
+    // report the launches that did work, not the no-op tail queued behind the `done` poll
+    stats->extend_launches += std::min<uint64_t>(ext, c.iterations);
+    stats->shade_launches += std::min<uint64_t>(shd, c.iterations);
+    // only iterations that actually had rays count as launches of the dominant kernel
+    double me = 0.0, msd = 0.0;
+    size_t live_it = std::min<size_t>(timed_iters, c.iterations);
+    for (size_t i = 0; i < live_it; ++i) {
+      float a = 0.0f, b = 0.0f;
+      cudaEventElapsedTime(&a, L.events[ev_iter_base + 3 * i], L.events[ev_iter_base + 3 * i + 1]);
+      cudaEventElapsedTime(&b, L.events[ev_iter_base + 3 * i + 1], L.events[ev_iter_base + 3 * i + 2]);
+      me += a;
+      msd += b;
     }
+    if (live_it && live_it < c.iterations) {  // more iterations than event slots: scale up
+      double f = (double)c.iterations / (double)live_it;
+      me *= f;
+      msd *= f;
+    }
+    stats->ms_extend += me;
+    stats->ms_shade += msd;
+  }
+  return RT_OK;
+}
+
+// The megakernel engine: one launch of k_path renders the whole shard.  The kernel hands out work indices itself
+// (warps claim chunks of ctrl->cursor), so there is nothing for the host to do between the launch and the end.
+int run_megakernel(rt_scene* s, const rt_frame& fr_in, unsigned long long total, long long* d_accum, cudaStream_t st,
+                   uint32_t blocks_per_sm, rt_stats* stats) {
+  int rc;
+  if ((rc = ensure_runtime(s)) != RT_OK) return rc;
+  rt_frame fr = fr_in;
+  fr.sort_enabled = 0;
+  fr.sample_major = 0;  // 32 consecutive work indices = 32 samples of one pixel: a freshly filled warp runs in lockstep
+  rt_scene::Wavefront& L = s->wf;
+  EventPair ev;
+  if ((rc = ev.create()) != RT_OK) return rc;
+  CUDA_TRY(cudaEventRecord(ev.a, st));
+  rt::launch_init(L.ctrl, 0ull, total, st);
+  rt::launch_path(s->dev, fr, L.ctrl, d_accum, total, persistent_grid(s, s->path_blocks_per_sm, blocks_per_sm), st);
+  CUDA_TRY(cudaMemcpyAsync(L.h_ctrl, L.ctrl, sizeof(rt_ctrl), cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaEventRecord(ev.b, st));
+  CUDA_TRY(cudaStreamSynchronize(st));
+  CUDA_TRY(cudaGetLastError());
+  const rt_ctrl& c = *L.h_ctrl;
+  if (c.cursor < c.total) return fail(RT_ERR_CUDA, "megakernel ended before all work was claimed");
+  if (c.n_samples != total) return fail(RT_ERR_CUDA, "megakernel: work items started != work items in the shard");
+  if (stats) {
+    float ms = 0.0f;
+    cudaEventElapsedTime(&ms, ev.a, ev.b);
+    stats->ms_total += ms;
+    stats->ms_extend += ms;  // closest hit and shading are one kernel here
+    stats_from_ctrl(c, stats);
+    stats->iterations += 1;
+    stats->kernel_launches += 2;
+    stats->extend_launches += 1;
   }
   return RT_OK;
 }
@@ -524,7 +506,7 @@ int run_branching(rt_scene* s, const rt_frame& fr_in, unsigned long long total, 
   while ((P + (D - 1) * S * P) * 48ull > (4ull << 30) && P > 4096) P /= 2;
   P = std::max<uint64_t>(128, P / 128 * 128);
   fr.capacity = (uint32_t)P;
-  if ((rc = ensure_lane(s, 0, fr.capacity)) != RT_OK) return rc;
+  if ((rc = ensure_wavefront(s, fr.capacity)) != RT_OK) return rc;
   const uint64_t slots = P + (D - 1) * S * P;
   for (auto& b : s->d_tree)
     if ((rc = ensure_buf(b, slots * 16)) != RT_OK) return rc;
@@ -532,7 +514,8 @@ int run_branching(rt_scene* s, const rt_frame& fr_in, unsigned long long total, 
   auto at = [&](uint64_t off) {
     return rt::rt_paths{(float4*)s->d_tree[0].p + off, (float4*)s->d_tree[1].p + off, (float4*)s->d_tree[2].p + off};
   };
-  rt_scene::Lane& L = s->lanes[0];
+  rt_scene::Wavefront& L = s->wf;
+  const uint32_t grid = persistent_grid(s, s->trace_blocks_per_sm, 0);
   EventPair ev;
   if ((rc = ev.create()) != RT_OK) return rc;
   cudaEvent_t e0 = ev.a, e1 = ev.b;
@@ -560,7 +543,7 @@ int run_branching(rt_scene* s, const rt_frame& fr_in, unsigned long long total, 
     rt::rt_paths nxt = at((uint64_t)d + 1 < D ? level_base(d + 1) : 0);  // the last level has no children
     rt::launch_set_window(L.ctrl, n_cont, n_new, st);
     if (n_new) rt::launch_raygen(fr, L.ctrl, cur, st);
-    rt::launch_trace(s->dev, fr, L.ctrl, cur, L.hits, L.sort, false, s->persistent_blocks, st);
+    rt::launch_trace(s->dev, fr, L.ctrl, cur, L.hits, L.sort, false, grid, st);
     rt::launch_sort(s->dev, fr, L.ctrl, L.hits, L.queues, st);
     for (uint32_t b = 0; b < (uint32_t)S; ++b) {
       fr.branch = b;
@@ -594,12 +577,34 @@ int run_branching(rt_scene* s, const rt_frame& fr_in, unsigned long long total, 
   return RT_OK;
 }
 
-int default_lanes() {
-  if (const char* e = std::getenv("RT_LANES")) return std::max(1, std::min(RT_MAX_LANES, std::atoi(e)));
-  return RT_DEFAULT_LANES;
+// Last row of a column-major 4x4.  The forward transform must be affine exactly; a caller-supplied inverse (cgmath's
+// general Matrix4::invert, geometry.rs:168) comes out as (0,0,0,1) only up to rounding - w.w is minor3x3 * (1/det4) -
+// so a few ulps are accepted there and the row is then set to (0,0,0,1): the reference's divide by w (= 1 +- ulp)
+// is dropped, see DESIGN.md.
+bool affine_row(const float* m, bool exact) {
+  const float tol = exact ? 0.0f : 8.0f * 1.1920929e-7f;
+  return std::fabs(m[3]) <= tol && std::fabs(m[7]) <= tol && std::fabs(m[11]) <= tol && std::fabs(m[15] - 1.0f) <= tol;
+}
+void set_affine_row(float* m) {
+  m[3] = m[7] = m[11] = 0.0f;
+  m[15] = 1.0f;
+}
+
+// RT_ENGINE_AUTO.  Measured on B200: scenes without large instanced meshes (C1-C3) spend most of a
+// wavefront iteration moving path state through HBM, and the megakernel removes that; where traversal dominates and
+// the sorted wavefront keeps warps coherent (C4, C5) the wavefront engine stays ahead.
+uint32_t pick_engine(bool phong, bool counters, unsigned long long inst_tris) {
+  if (phong || counters) return RT_ENGINE_WAVEFRONT;
+  return inst_tris < 16384ull ? RT_ENGINE_MEGAKERNEL : RT_ENGINE_WAVEFRONT;
 }
 
 }  // namespace
+
+// Nothing may throw across the C ABI: std::bad_alloc / length_error from a huge or hostile asset becomes an error code.
+#define RT_CATCH(who)                                                                                   \
+  catch (const std::bad_alloc&) { return fail(RT_ERR_IO, who ": out of memory"); }                      \
+  catch (const std::exception& e) { return fail(RT_ERR_INVALID, std::string(who ": ") + e.what()); }    \
+  catch (...) { return fail(RT_ERR_INVALID, who ": unknown exception"); }
 
 // ====================================================================== C ABI
 extern "C" {
@@ -627,7 +632,8 @@ void rt_scene_destroy(rt_scene* s) {
     free_buf(s->d_mats); free_buf(s->d_textures); free_buf(s->d_texels); free_buf(s->d_planes); free_buf(s->d_guards); free_buf(s->d_guard_list);
     free_buf(s->d_accum); free_buf(s->d_linear); free_buf(s->d_rgb8); free_buf(s->d_dbg);
     for (auto& b : s->d_tree) free_buf(b);
-    for (auto& L : s->lanes) {
+    {
+      rt_scene::Wavefront& L = s->wf;
       if (L.ctrl) cudaFree(L.ctrl);
       if (L.sort.hist) cudaFree(L.sort.hist);
       if (L.sort.cursor) cudaFree(L.sort.cursor);
@@ -636,16 +642,13 @@ void rt_scene_destroy(rt_scene* s) {
       if (L.h_done) cudaFreeHost(L.h_done);
       for (auto e : L.events) cudaEventDestroy(e);
       for (auto e : L.poll_ev) if (e) cudaEventDestroy(e);
-      if (L.end_ev) cudaEventDestroy(L.end_ev);
-      if (L.stream) cudaStreamDestroy(L.stream);
     }
-    if (s->begin_ev) cudaEventDestroy(s->begin_ev);
     if (s->own_stream) cudaStreamDestroy(s->own_stream);
   }
   delete s;
 }
 
-int rt_add_texture(rt_scene* s, const uint8_t* rgb8, uint32_t w, uint32_t h) {
+int rt_add_texture(rt_scene* s, const uint8_t* rgb8, uint32_t w, uint32_t h) try {
   if (!s || !rgb8 || !w || !h) return fail(RT_ERR_INVALID, "rt_add_texture: bad argument");
   rt::HostTexture t;
   t.w = w;
@@ -657,17 +660,19 @@ int rt_add_texture(rt_scene* s, const uint8_t* rgb8, uint32_t w, uint32_t h) {
   s->lowered = false;
   return (int)s->textures.size() - 1;
 }
+RT_CATCH("rt_add_texture")
 
-int rt_add_material(rt_scene* s, const rt_material_desc* d) {
+int rt_add_material(rt_scene* s, const rt_material_desc* d) try {
   if (!s || !d) return fail(RT_ERR_INVALID, "rt_add_material: bad argument");
   if (d->tag > RT_MAT_ISOTROPIC) return fail(RT_ERR_INVALID, "rt_add_material: unknown material tag");
   s->materials.push_back(*d);
   s->lowered = false;
   return (int)s->materials.size() - 1;
 }
+RT_CATCH("rt_add_material")
 
 int rt_add_mesh(rt_scene* s, const float* pos, const float* nrm, const float* uv, uint32_t nverts, const uint32_t* idx,
-                uint32_t ntris) {
+                uint32_t ntris) try {
   if (!s || !pos || !nrm || !uv || !idx || !nverts || !ntris) return fail(RT_ERR_INVALID, "rt_add_mesh: bad argument");
   for (size_t i = 0; i < 3 * (size_t)ntris; ++i)
     if (idx[i] >= nverts) return fail(RT_ERR_INVALID, "rt_add_mesh: index out of range");
@@ -681,13 +686,13 @@ int rt_add_mesh(rt_scene* s, const float* pos, const float* nrm, const float* uv
   s->lowered = false;
   return (int)s->meshes.size() - 1;
 }
+RT_CATCH("rt_add_mesh")
 
-int rt_add_instance(rt_scene* s, int mesh, const float xform[16], const float* inv_xform, int material, const int tex[5]) {
+int rt_add_instance(rt_scene* s, int mesh, const float xform[16], const float* inv_xform, int material, const int tex[5]) try {
   if (!s || !xform) return fail(RT_ERR_INVALID, "rt_add_instance: bad argument");
   if (mesh < 0 || mesh >= (int)s->meshes.size()) return fail(RT_ERR_INVALID, "rt_add_instance: bad mesh id");
   if (material >= (int)s->materials.size()) return fail(RT_ERR_INVALID, "rt_add_instance: bad material id");
-  if (xform[3] != 0.0f || xform[7] != 0.0f || xform[11] != 0.0f || xform[15] != 1.0f ||
-      (inv_xform && (inv_xform[3] != 0.0f || inv_xform[7] != 0.0f || inv_xform[11] != 0.0f || inv_xform[15] != 1.0f)))
+  if (!affine_row(xform, true) || (inv_xform && !affine_row(inv_xform, false)))
     return fail(RT_ERR_UNSUPPORTED, "rt_add_instance: only affine transforms (last row 0 0 0 1) are supported");
   rt::HostObject o;
   o.kind = RT_OBJ_MESH;
@@ -695,6 +700,7 @@ int rt_add_instance(rt_scene* s, int mesh, const float xform[16], const float* i
   std::memcpy(o.xform, xform, 64);
   if (inv_xform) {
     std::memcpy(o.inv_xform, inv_xform, 64);
+    set_affine_row(o.inv_xform);
   } else if (!rt::invert_affine_cofactor(xform, o.inv_xform)) {
     return fail(RT_ERR_INVALID, "rt_add_instance: transform is singular (the reference panics here, geometry.rs:168)");
   }
@@ -708,6 +714,7 @@ int rt_add_instance(rt_scene* s, int mesh, const float xform[16], const float* i
   s->lowered = false;
   return (int)s->objects.size() - 1;
 }
+RT_CATCH("rt_add_instance")
 
 static int add_simple(rt_scene* s, rt::HostObject& o, int material, const char* who) {
   if (material < 0 || material >= (int)s->materials.size()) return fail(RT_ERR_INVALID, std::string(who) + ": bad material id");
@@ -716,7 +723,7 @@ static int add_simple(rt_scene* s, rt::HostObject& o, int material, const char* 
   s->lowered = false;
   return (int)s->objects.size() - 1;
 }
-int rt_add_sphere(rt_scene* s, const float c[3], float radius, int material) {
+int rt_add_sphere(rt_scene* s, const float c[3], float radius, int material) try {
   if (!s || !c) return fail(RT_ERR_INVALID, "rt_add_sphere: bad argument");
   rt::HostObject o;
   o.kind = RT_OBJ_SPHERE;
@@ -724,7 +731,8 @@ int rt_add_sphere(rt_scene* s, const float c[3], float radius, int material) {
   o.radius = radius;
   return add_simple(s, o, material, "rt_add_sphere");
 }
-int rt_add_triangle(rt_scene* s, const float a[3], const float b[3], const float c[3], int material) {
+RT_CATCH("rt_add_sphere")
+int rt_add_triangle(rt_scene* s, const float a[3], const float b[3], const float c[3], int material) try {
   if (!s || !a || !b || !c) return fail(RT_ERR_INVALID, "rt_add_triangle: bad argument");
   rt::HostObject o;
   o.kind = RT_OBJ_TRIANGLE;
@@ -733,7 +741,8 @@ int rt_add_triangle(rt_scene* s, const float a[3], const float b[3], const float
   std::memcpy(o.c, c, 12);
   return add_simple(s, o, material, "rt_add_triangle");
 }
-int rt_add_plane(rt_scene* s, const float p[3], const float n[3], int material) {
+RT_CATCH("rt_add_triangle")
+int rt_add_plane(rt_scene* s, const float p[3], const float n[3], int material) try {
   if (!s || !p || !n) return fail(RT_ERR_INVALID, "rt_add_plane: bad argument");
   rt::HostObject o;
   o.kind = RT_OBJ_PLANE;
@@ -741,7 +750,8 @@ int rt_add_plane(rt_scene* s, const float p[3], const float n[3], int material) 
   std::memcpy(o.b, n, 12);
   return add_simple(s, o, material, "rt_add_plane");
 }
-int rt_add_volume_sphere(rt_scene* s, const float c[3], float radius, float density, int phase_material) {
+RT_CATCH("rt_add_plane")
+int rt_add_volume_sphere(rt_scene* s, const float c[3], float radius, float density, int phase_material) try {
   if (!s || !c) return fail(RT_ERR_INVALID, "rt_add_volume_sphere: bad argument");
   rt::HostObject o;
   o.kind = RT_OBJ_VOLUME;
@@ -753,28 +763,31 @@ int rt_add_volume_sphere(rt_scene* s, const float c[3], float radius, float dens
   if (rc >= 0) s->n_volumes++;
   return rc;
 }
+RT_CATCH("rt_add_volume_sphere")
 
 int rt_add_volume_mesh(rt_scene* s, int mesh, const float xform[16], const float* inv_xform, float density,
-                       int phase_material) {
+                       int phase_material) try {
   if (!s || !xform) return fail(RT_ERR_INVALID, "rt_add_volume_mesh: bad argument");
   if (mesh < 0 || mesh >= (int)s->meshes.size()) return fail(RT_ERR_INVALID, "rt_add_volume_mesh: bad mesh id");
-  if (xform[3] != 0.0f || xform[7] != 0.0f || xform[11] != 0.0f || xform[15] != 1.0f ||
-      (inv_xform && (inv_xform[3] != 0.0f || inv_xform[7] != 0.0f || inv_xform[11] != 0.0f || inv_xform[15] != 1.0f)))
+  if (!affine_row(xform, true) || (inv_xform && !affine_row(inv_xform, false)))
     return fail(RT_ERR_UNSUPPORTED, "rt_add_volume_mesh: only affine transforms (last row 0 0 0 1) are supported");
   rt::HostObject o;
   o.kind = RT_OBJ_VOLUME_MESH;
   o.mesh = mesh;
   std::memcpy(o.xform, xform, 64);
-  if (inv_xform) std::memcpy(o.inv_xform, inv_xform, 64);
-  else if (!rt::invert_affine_cofactor(xform, o.inv_xform)) return fail(RT_ERR_INVALID, "rt_add_volume_mesh: transform is singular");
+  if (inv_xform) {
+    std::memcpy(o.inv_xform, inv_xform, 64);
+    set_affine_row(o.inv_xform);
+  } else if (!rt::invert_affine_cofactor(xform, o.inv_xform)) return fail(RT_ERR_INVALID, "rt_add_volume_mesh: transform is singular");
   o.density = density;
   o.vol_index = s->n_volumes;
   int rc = add_simple(s, o, phase_material, "rt_add_volume_mesh");
   if (rc >= 0) s->n_volumes++;
   return rc;
 }
+RT_CATCH("rt_add_volume_mesh")
 
-int rt_scene_upload(rt_scene* s) {
+int rt_scene_upload(rt_scene* s) try {
   if (!s || !s->lowered) return fail(RT_ERR_NOT_COMMITTED, "rt_scene_upload: scene has not been lowered (call rt_commit)");
   CUDA_TRY(cudaSetDevice(s->device));
   const rt::Lowered& L = s->low;
@@ -807,8 +820,9 @@ int rt_scene_upload(rt_scene* s) {
   s->committed = true;
   return RT_OK;
 }
+RT_CATCH("rt_scene_upload")
 
-int rt_scene_lower(rt_scene* s, rt_lower_info* info) {
+int rt_scene_lower(rt_scene* s, rt_lower_info* info) try {
   if (!s) return fail(RT_ERR_INVALID, "scene is NULL");
   std::string err;
   int rc = rt::lower_scene(s->textures, s->materials, s->meshes, s->objects, s->low, err);
@@ -836,8 +850,9 @@ int rt_scene_lower(rt_scene* s, rt_lower_info* info) {
   }
   return RT_OK;
 }
+RT_CATCH("rt_scene_lower")
 
-int rt_commit(rt_scene* s, int device) {
+int rt_commit(rt_scene* s, int device) try {
   if (!s) return fail(RT_ERR_INVALID, "scene is NULL");
   int n = 0;
   cudaError_t e = cudaGetDeviceCount(&n);
@@ -851,13 +866,14 @@ int rt_commit(rt_scene* s, int device) {
   s->device = device;
   return rt_scene_upload(s);
 }
+RT_CATCH("rt_commit")
 
 uint64_t rt_scene_device_bytes(const rt_scene* s) { return s && s->lowered ? s->low.bytes() : 0; }
 
 size_t rt_accum_bytes(uint32_t width, uint32_t height) { return (size_t)width * height * 4 * sizeof(long long); }
 
 int rt_render_accum(rt_scene* s, const rt_camera* cam, const rt_render_opts* opts, void* d_accum, void* stream,
-                    rt_stats* stats) {
+                    rt_stats* stats) try {
   int rc = set_device(s);
   if (rc != RT_OK) return rc;
   if ((rc = check_camera(cam)) != RT_OK) return rc;
@@ -881,38 +897,47 @@ int rt_render_accum(rt_scene* s, const rt_camera* cam, const rt_render_opts* opt
   // NULL means the (legacy) default stream, as documented: work must be ordered after whatever the caller has
   // already enqueued there (e.g. the memset of d_accum), which a private non-blocking stream would not be
   cudaStream_t st = (cudaStream_t)stream;
-  // Secondary-ray sorting (k_shade keys -> k_raysort_*).  It pays where traversal dominates: on C4 k_trace drops from
-  // 1230 to 990 us per 8 Mi rays for ~150 us of sorting (+9 %); on C2 (two 240-triangle teapots in a closed box, 5 nodes
-  // per ray) the indirection costs more than it saves (-14 %).  Hence the switch on the amount of instanced geometry.
+  for (uint32_t r : o.reserved)
+    if (r) return fail(RT_ERR_INVALID, "rt_render_opts.reserved must be zero");
+  if (o.engine > RT_ENGINE_MEGAKERNEL) return fail(RT_ERR_INVALID, "unknown engine");
+  if (o.ray_sort > RT_RAYSORT_ON) return fail(RT_ERR_INVALID, "unknown ray_sort");
+  unsigned long long inst_tris = 0;
+  for (const auto& ob : s->objects)
+    if (ob.kind == RT_OBJ_MESH) inst_tris += s->meshes[ob.mesh].n_reachable;
+  // Secondary-ray sorting (k_shade keys -> k_raysort_*), wavefront engine.  It pays where traversal dominates: on C4
+  // k_trace drops from 1230 to 990 us per 8 Mi rays for ~150 us of sorting (+9 %); on C2 (two 240-triangle teapots in a
+  // closed box, 5 nodes per ray) the indirection costs more than it saves (-14 %).  Hence the switch on the amount of
+  // instanced geometry.
   {
-    int want = RT_DEFAULT_RAY_SORT;
-    if (const char* e = std::getenv("RT_RAY_SORT")) want = std::atoi(e);
-    unsigned long long inst_tris = 0;
-    for (const auto& o : s->objects)
-      if (o.kind == RT_OBJ_MESH) inst_tris += s->meshes[o.mesh].n_reachable;
-    bool worth = want == 2 || (want == 1 && inst_tris >= 16384ull);
+    bool worth = o.ray_sort == RT_RAYSORT_ON || (o.ray_sort == RT_RAYSORT_AUTO && inst_tris >= 16384ull);
     fr.sort_enabled = (worth && s->low.tlas_root != RT_ENTRY_NONE) ? 1u : 0u;
-    int cells = 32;
-    if (const char* e = std::getenv("RT_SORT_CELLS")) cells = std::max(1, std::min(1024, std::atoi(e)));
+    const int cells = 32;    // cells per axis of the TLAS box (measured: 8 / 16 / 32 / 64 -> 2253 / 2314 / 2348 / 2284 Msamples/s)
     fr.sort_cells_m1 = (float)(cells - 1);
-    fr.sort_use_octant = 2;  // 0: cell only, 1: + octant, 2: + octant and dominant axis (measured best)
-    if (const char* e = std::getenv("RT_SORT_OCTANT")) fr.sort_use_octant = (uint32_t)std::max(0, std::min(2, std::atoi(e)));
-    float grow = 0.0f;  // RT_SORT_GROW: enlarge the cell grid beyond the TLAS box by this fraction of its extent per side
-    if (const char* e = std::getenv("RT_SORT_GROW")) grow = (float)std::atof(e);
+    fr.sort_use_octant = 2;  // direction class = octant + dominant axis (measured best of: none, octant, octant + axis)
     for (int k = 0; k < 3; ++k) {
       float ext = s->low.tlas_max[k] - s->low.tlas_min[k];
-      fr.sort_min[k] = s->low.tlas_min[k] - grow * ext;
-      ext *= 1.0f + 2.0f * grow;
+      fr.sort_min[k] = s->low.tlas_min[k];
       fr.sort_scale[k] = ext > 0.0f ? (float)cells / ext : 0.0f;
     }
   }
-  if (fr.path_samples > 1) return run_branching(s, fr, total, (long long*)d_accum, st, stats);
-  return run_wavefront(s, fr, total, (long long*)d_accum, (o.flags & RT_OPT_COUNTERS) != 0,
-                       (o.flags & RT_OPT_NO_EVENTS) == 0, st, default_lanes(), stats);
+  const bool counters = (o.flags & RT_OPT_COUNTERS) != 0;
+  if (fr.path_samples > 1) {
+    if (o.engine == RT_ENGINE_MEGAKERNEL) return fail(RT_ERR_UNSUPPORTED, "path_samples > 1 runs on the wavefront engine only");
+    return run_branching(s, fr, total, (long long*)d_accum, st, stats);
+  }
+  // Engine.  The debug modes and the device counters exist in the wavefront engine only.
+  uint32_t engine = o.engine;
+  if (engine == RT_ENGINE_MEGAKERNEL && (fr.phong || counters))
+    return fail(RT_ERR_UNSUPPORTED, "ShadingMode::Phong and RT_OPT_COUNTERS run on the wavefront engine only");
+  if (engine == RT_ENGINE_AUTO) engine = pick_engine(fr.phong != 0, counters, inst_tris);
+  if (engine == RT_ENGINE_MEGAKERNEL) return run_megakernel(s, fr, total, (long long*)d_accum, st, o.blocks_per_sm, stats);
+  return run_wavefront(s, fr, total, (long long*)d_accum, counters, (o.flags & RT_OPT_NO_EVENTS) == 0, st, o.blocks_per_sm,
+                       stats);
 }
+RT_CATCH("rt_render_accum")
 
 int rt_resolve(rt_scene* s, const rt_camera* cam, const void* d_accum, uint32_t total_spp, float* d_out_linear,
-               uint8_t* d_out_rgb8, void* stream) {
+               uint8_t* d_out_rgb8, void* stream) try {
   int rc = set_device(s);
   if (rc != RT_OK) return rc;
   if (!cam || !d_accum || !total_spp) return fail(RT_ERR_INVALID, "rt_resolve: bad argument");
@@ -922,9 +947,10 @@ int rt_resolve(rt_scene* s, const rt_camera* cam, const void* d_accum, uint32_t 
   CUDA_TRY(cudaGetLastError());
   return RT_OK;
 }
+RT_CATCH("rt_resolve")
 
 int rt_render(rt_scene* s, const rt_camera* cam, const rt_render_opts* opts, float* out_linear, uint8_t* out_rgb8,
-              rt_stats* stats) {
+              rt_stats* stats) try {
   int rc = set_device(s);
   if (rc != RT_OK) return rc;
   if ((rc = check_camera(cam)) != RT_OK) return rc;
@@ -970,6 +996,7 @@ int rt_render(rt_scene* s, const rt_camera* cam, const rt_render_opts* opts, flo
   if (stats) *stats = local;
   return RT_OK;
 }
+RT_CATCH("rt_render")
 
 // ---- parity hooks: one k_extend launch in debug mode, results copied back
 static int trace_common(rt_scene* s, const rt_frame& fr, unsigned long long total, uint32_t n, const float* ray_od,
@@ -977,7 +1004,7 @@ static int trace_common(rt_scene* s, const rt_frame& fr, unsigned long long tota
                         int32_t* frontface, float* ray_out) {
   int rc = ensure_wavefront(s, fr.capacity);
   if (rc != RT_OK) return rc;
-  rt_scene::Lane& L0 = s->lanes[0];
+  rt_scene::Wavefront& L0 = s->wf;
   cudaStream_t st = s->own_stream;
   const size_t cap = fr.capacity;
   if ((rc = ensure_buf(s->d_dbg, cap * 36)) != RT_OK) return rc;
@@ -1009,7 +1036,7 @@ static int trace_common(rt_scene* s, const rt_frame& fr, unsigned long long tota
   if (ray_od) CUDA_TRY(cudaMemcpyAsync(&L0.ctrl->n_next, &n, 4, cudaMemcpyHostToDevice, st));
   rt::launch_advance(L0.ctrl, f2.capacity, st);
   if (!ray_od) rt::launch_raygen(f2, L0.ctrl, L0.paths[0], st);
-  rt::launch_trace(s->dev, f2, L0.ctrl, L0.paths[0], L0.hits, L0.sort, false, s->persistent_blocks, st);
+  rt::launch_trace(s->dev, f2, L0.ctrl, L0.paths[0], L0.hits, L0.sort, false, persistent_grid(s, s->trace_blocks_per_sm, 0), st);
   rt::launch_surface(s->dev, f2, L0.ctrl, L0.paths[0], L0.hits, dbg, st);
   CUDA_TRY(cudaGetLastError());
   std::vector<float> H0((size_t)n * 4), H1((size_t)n * 4), HH((size_t)n * 4);
@@ -1058,7 +1085,7 @@ static int trace_common(rt_scene* s, const rt_frame& fr, unsigned long long tota
 }
 
 int rt_trace_primary(rt_scene* s, const rt_camera* cam, uint64_t seed, uint32_t sample, int32_t* obj_id,
-                     int32_t* prim_id, float* t, float* normal_xyz, float* ray_od) {
+                     int32_t* prim_id, float* t, float* normal_xyz, float* ray_od) try {
   int rc = set_device(s);
   if (rc != RT_OK) return rc;
   if ((rc = check_camera(cam)) != RT_OK) return rc;
@@ -1074,10 +1101,11 @@ int rt_trace_primary(rt_scene* s, const rt_camera* cam, uint64_t seed, uint32_t 
   return trace_common(s, fr, total, (uint32_t)total, nullptr, obj_id, prim_id, t, normal_xyz, nullptr, nullptr, nullptr,
                       ray_od);
 }
+RT_CATCH("rt_trace_primary")
 
 int rt_intersect_rays(rt_scene* s, uint64_t seed, uint32_t n, const float* ray_od, float t_min, float t_max,
                       int32_t* obj_id, int32_t* prim_id, float* t, float* normal_xyz, float* hitpoint_xyz, float* uv,
-                      int32_t* frontface) {
+                      int32_t* frontface) try {
   int rc = set_device(s);
   if (rc != RT_OK) return rc;
   if (!ray_od) return fail(RT_ERR_INVALID, "rt_intersect_rays: ray_od is NULL");
@@ -1094,15 +1122,17 @@ int rt_intersect_rays(rt_scene* s, uint64_t seed, uint32_t n, const float* ray_o
   fr.capacity = (n + 127) / 128 * 128;
   return trace_common(s, fr, 0, n, ray_od, obj_id, prim_id, t, normal_xyz, hitpoint_xyz, uv, frontface, nullptr);
 }
+RT_CATCH("rt_intersect_rays")
 
 // ---- assets
-int rt_obj_parse(const char* text, size_t len, rt_obj_mesh* out) {
+int rt_obj_parse(const char* text, size_t len, rt_obj_mesh* out) try {
   if (!text || !out) return fail(RT_ERR_INVALID, "rt_obj_parse: bad argument");
   std::string err;
   int rc = rt::obj_parse(text, len, out, err);
   return rc == RT_OK ? RT_OK : fail(rc, err);
 }
-int rt_obj_load(const char* path, rt_obj_mesh* out) {
+RT_CATCH("rt_obj_parse")
+int rt_obj_load(const char* path, rt_obj_mesh* out) try {
   if (!path || !out) return fail(RT_ERR_INVALID, "rt_obj_load: bad argument");
   FILE* f = std::fopen(path, "rb");
   if (!f) return fail(RT_ERR_IO, std::string("cannot open ") + path);
@@ -1113,46 +1143,53 @@ int rt_obj_load(const char* path, rt_obj_mesh* out) {
   std::fclose(f);
   return rt_obj_parse(data.data(), data.size(), out);
 }
+RT_CATCH("rt_obj_load")
 void rt_obj_free(rt_obj_mesh* m) {
   if (!m) return;
   std::free(m->pos); std::free(m->nrm); std::free(m->uv); std::free(m->idx);
   std::memset(m, 0, sizeof *m);
 }
-int rt_tga_decode(const uint8_t* bytes, size_t len, uint8_t** rgb, uint32_t* w, uint32_t* h) {
+int rt_tga_decode(const uint8_t* bytes, size_t len, uint8_t** rgb, uint32_t* w, uint32_t* h) try {
   if (!bytes || !rgb || !w || !h) return fail(RT_ERR_INVALID, "rt_tga_decode: bad argument");
   std::string err;
   int rc = rt::tga_decode(bytes, len, rgb, w, h, err);
   return rc == RT_OK ? RT_OK : fail(rc, err);
 }
-int rt_tga_encode_rgb8(const uint8_t* rgb, uint32_t w, uint32_t h, uint8_t** bytes, size_t* len) {
+RT_CATCH("rt_tga_decode")
+int rt_tga_encode_rgb8(const uint8_t* rgb, uint32_t w, uint32_t h, uint8_t** bytes, size_t* len) try {
   int rc = rt::tga_encode_rgb8(rgb, w, h, bytes, len);
   return rc == RT_OK ? RT_OK : fail(rc, "rt_tga_encode_rgb8: bad argument");
 }
-int rt_png_decode(const uint8_t* bytes, size_t len, uint8_t** rgb, uint32_t* w, uint32_t* h) {
+RT_CATCH("rt_tga_encode_rgb8")
+int rt_png_decode(const uint8_t* bytes, size_t len, uint8_t** rgb, uint32_t* w, uint32_t* h) try {
   if (!bytes || !rgb || !w || !h) return fail(RT_ERR_INVALID, "rt_png_decode: bad argument");
   std::string err;
   int rc = rt::png_decode(bytes, len, rgb, w, h, err);
   return rc == RT_OK ? RT_OK : fail(rc, err);
 }
-int rt_jpeg_decode(const uint8_t* bytes, size_t len, uint8_t** rgb, uint32_t* w, uint32_t* h) {
+RT_CATCH("rt_png_decode")
+int rt_jpeg_decode(const uint8_t* bytes, size_t len, uint8_t** rgb, uint32_t* w, uint32_t* h) try {
   if (!bytes || !rgb || !w || !h) return fail(RT_ERR_INVALID, "rt_jpeg_decode: bad argument");
   std::string err;
   int rc = rt::jpeg_decode(bytes, len, rgb, w, h, err);
   return rc == RT_OK ? RT_OK : fail(rc, err);
 }
-int rt_png_encode_rgb8(const uint8_t* rgb, uint32_t w, uint32_t h, uint8_t** bytes, size_t* len) {
+RT_CATCH("rt_jpeg_decode")
+int rt_png_encode_rgb8(const uint8_t* rgb, uint32_t w, uint32_t h, uint8_t** bytes, size_t* len) try {
   if (!bytes || !len) return fail(RT_ERR_INVALID, "rt_png_encode_rgb8: bad argument");
   int rc = rt::png_encode_rgb8(rgb, w, h, bytes, len);
   return rc == RT_OK ? RT_OK : fail(rc, "rt_png_encode_rgb8: bad argument");
 }
+RT_CATCH("rt_png_encode_rgb8")
 void rt_free(void* p) { std::free(p); }
 
-int rt_mesh_reachability(const float* pos, uint32_t nverts, const uint32_t* idx, uint32_t ntris, uint8_t* mask) {
+int rt_mesh_reachability(const float* pos, uint32_t nverts, const uint32_t* idx, uint32_t ntris, uint8_t* mask) try {
   if (!pos || !idx || !mask) return fail(RT_ERR_INVALID, "rt_mesh_reachability: bad argument");
   for (size_t i = 0; i < 3 * (size_t)ntris; ++i)
     if (idx[i] >= nverts) return fail(RT_ERR_INVALID, "rt_mesh_reachability: index out of range");
   rt::mesh_reachability(pos, idx, ntris, mask);
   return RT_OK;
 }
+RT_CATCH("rt_mesh_reachability")
 
 }  // extern "C"

@@ -26,6 +26,16 @@
 #ifndef RT_OCTANT_SORT
 #define RT_OCTANT_SORT 1
 #endif
+// TLAS nodes (32 B each, breadth-first from the root) every persistent block keeps in shared memory; 0 = none.
+// Must be even (child pairs).
+#ifndef RT_TLAS_SMEM
+#define RT_TLAS_SMEM 128
+#endif
+// k_trace claims its next chunk of ray indices while it traverses the current one, so the latency of the
+// single-address atomic is hidden behind the traversal
+#ifndef RT_CLAIM_PREFETCH
+#define RT_CLAIM_PREFETCH 1
+#endif
 #ifndef RT_EXTEND_MIN_BLOCKS
 #define RT_EXTEND_MIN_BLOCKS 8  // 64 registers per thread -> 32 resident warps per SM
 #endif

@@ -29,6 +29,7 @@
 #include "rt_device_math.cuh"
 #include "rt_traverse.cuh"
 #include "rt_materials.cuh"
+#include "rt_shade.cuh"
 
 namespace rt {
 
@@ -97,6 +98,10 @@ template <bool COUNT, bool VOLMESH>
 __global__ void __launch_bounds__(RT_BLOCK, RT_EXTEND_MIN_BLOCKS) k_trace(rt_dev_scene sc, rt_frame fr, rt_ctrl* __restrict__ ctrl,
                                                                         rt_paths cur, rt_hits hits, const uint32_t* __restrict__ order) {
   __shared__ __align__(8) uint32_t sstack[(RT_SMEM_STACK + 6 + (VOLMESH ? 6 : 0)) * RT_BLOCK];
+#if RT_TLAS_SMEM
+  __shared__ float4 s_tlas[RT_TLAS_SMEM * RT_NODE_QUADS];
+  load_tlas_cache(sc, s_tlas);
+#endif
   const uint32_t n_rays = ctrl->n_rays;
   const uint32_t n_sorted = fr.sort_enabled ? ctrl->n_cont : 0u;  // continuing rays are visited in sorted order
   const uint32_t lane = threadIdx.x & 31u;
@@ -106,6 +111,9 @@ __global__ void __launch_bounds__(RT_BLOCK, RT_EXTEND_MIN_BLOCKS) k_trace(rt_dev
   T.sbase = (uint32_t)__cvta_generic_to_shared(sstack) + threadIdx.x * 4u;
   T.wbase = (uint32_t)__cvta_generic_to_shared(sstack) + RT_SMEM_STACK * (RT_BLOCK * 4u) + threadIdx.x * 4u;
   T.lstack = lstack;
+#if RT_TLAS_SMEM
+  T.tbase = (uint32_t)__cvta_generic_to_shared(s_tlas);
+#endif
   T.t_min = fr.t_min; T.t_max = fr.t_max;
   T.k0 = fr.k0; T.k1 = fr.k1;
   T.qA = cur.A; T.qB = cur.B; T.qC = cur.C;
@@ -113,6 +121,13 @@ __global__ void __launch_bounds__(RT_BLOCK, RT_EXTEND_MIN_BLOCKS) k_trace(rt_dev
   bool have = false, fin = false;
   uint32_t c_next = 0, c_end = 0;  // this warp's claimed chunk of ray indices (warp uniform)
   bool exhausted = false;          // the queue has no more chunks (warp uniform)
+#if RT_CLAIM_PREFETCH
+  // the chunk after the current one is claimed ahead of time (lane 0 holds the result): by the time the warp needs
+  // it, the atomic has long returned.  Each warp ends up with one claim past the end of the queue, which is harmless
+  // (k_advance resets the cursor every iteration).
+  uint32_t pf = 0;
+  if (lane == 0) pf = atomicAdd(&ctrl->next_ray, (uint32_t)RT_FETCH_CHUNK);
+#endif
 
   for (;;) {
     // ---- retire finished lanes: the compact hit record is all k_shade needs to redo the rest
@@ -140,9 +155,14 @@ __global__ void __launch_bounds__(RT_BLOCK, RT_EXTEND_MIN_BLOCKS) k_trace(rt_dev
     if ((need == FULL || __popc(need) >= RT_REFILL_MIN) && !(exhausted && c_next >= c_end)) {
       uint32_t n_need = __popc(need);
       if (c_next >= c_end && !exhausted) {
+#if RT_CLAIM_PREFETCH
+        uint32_t base = __shfl_sync(FULL, pf, 0);
+        if (lane == 0 && base + RT_FETCH_CHUNK < n_rays) pf = atomicAdd(&ctrl->next_ray, (uint32_t)RT_FETCH_CHUNK);
+#else
         uint32_t base = 0;
         if (lane == 0) base = atomicAdd(&ctrl->next_ray, (uint32_t)RT_FETCH_CHUNK);
         base = __shfl_sync(FULL, base, 0);
+#endif
         c_next = base;
         c_end = min(base + (uint32_t)RT_FETCH_CHUNK, n_rays);
         if (base + RT_FETCH_CHUNK >= n_rays) exhausted = true;
@@ -298,108 +318,20 @@ __global__ void __launch_bounds__(RT_BLOCK, RT_SHADE_MIN_BLOCKS) k_shade(rt_dev_
   if (j < count) {
     uint32_t slot = RT_LDS(&queues[(size_t)cls * fr.capacity + j]);
     float4 a = RT_LDS(&cur.A[slot]), bq = RT_LDS(&cur.B[slot]), c = RT_LDS(&cur.C[slot]);
-    f3 o = mk(a.x, a.y, a.z);
-    f3 d = mk(a.w, bq.x, bq.y);
-    f3 T = mk(bq.z, bq.w, c.x);
-    pixel = fbits(c.y);
-    sb = fbits(c.z);
-    if (MULTI) tree = fbits(c.w) * fr.path_samples + fr.branch;
-    uint32_t sample = sb & 0xFFFFFFu, bounce = sb >> 24;
-    // hit resolution: what the reference attaches to its RayHit
+    PathState p;
+    p.o = mk(a.x, a.y, a.z);
+    p.d = mk(a.w, bq.x, bq.y);
+    p.T = mk(bq.z, bq.w, c.x);
+    p.pixel = fbits(c.y);
+    p.sb = fbits(c.z);
+    p.tree = MULTI ? fbits(c.w) : 0u;
     float4 hr = RT_LDS(&hits.H[slot]);
     Best best;
     best.t = hr.x; best.u = hr.y; best.v = hr.z; best.prim = fbits(hr.w);
     best.obj = RT_LDS(&hits.obj[slot]);
-    Surface sf;
-    resolve_hit<COUNT>(sc, o, d, best, sf, ctrl->counters);
-    f3 hp = sf.hp, n = sf.n;
-    float4 h1 = make_float4(0.f, 0.f, sf.u, sf.v);
-    uint32_t meta = sf.meta;
-    bool front = (meta >> 3) & 1u;
-    uint32_t id = meta >> 4;
-
-    // material parameters
-    f3 albedo, emission;
-    float roughness, metallic;
-    if (cls == RT_CLASS_PARAM_TEX) {
-      // StaticMesh::get_material_at_uv, geometry.rs:259-269 (Q7 defaults)
-      uint32_t q = id * RT_OBJ_QUADS;
-      float4 m7 = ldq(sc.objects, q + 7), m8 = ldq(sc.objects, q + 8);
-      int ta = (int)fbits(m7.z), te = (int)fbits(m7.w), tm = (int)fbits(m8.x), tr = (int)fbits(m8.y);
-      float u = h1.z, v = h1.w;
-      albedo = ta >= 0 ? tex_sample(sc, ta, u, v) : mk(0.f, 0.f, 0.f);
-      emission = te >= 0 ? tex_sample(sc, te, u, v) : mk(0.f, 0.f, 0.f);
-      metallic = tm >= 0 ? tex_sample(sc, tm, u, v).x : 0.0f;
-      roughness = tr >= 0 ? tex_sample(sc, tr, u, v).x : 1.0f;
-      if (COUNT) atomicAdd(&ctrl->counters[5], (unsigned long long)((ta >= 0) + (te >= 0) + (tm >= 0) + (tr >= 0)));
-    } else {
-      float4 m0 = ldq(sc.mats, id * RT_MAT_QUADS), m1 = ldq(sc.mats, id * RT_MAT_QUADS + 1);
-      if (COUNT) atomicAdd(&ctrl->counters[6], 1ull);
-      albedo = mk(m0.x, m0.y, m0.z);
-      emission = mk(m1.x, m1.y, m1.z);
-      roughness = m0.w;
-      metallic = m1.w;
-    }
-
-    // emitted light reaches the pixel attenuated by the path throughput (tracing.rs:321)
-    if ((!MULTI || fr.branch == 0u) && (emission.x != 0.0f || emission.y != 0.0f || emission.z != 0.0f))
-      accum_add(accum, pixel, mulv(T, emission));
-
-    // scatter (materials.rs:33-166)
-    u4 r = philox4x32_10(pixel, sample, bounce, 0u, fr.k0, MULTI ? fr.k1 ^ (tree * 0x9E3779B9u) : fr.k1);
-    float u_choice = u01(r.x);
-    f3 ball = ball_from(r.y, r.z, r.w);
-    f3 dir, brdf;
-    float pdf;
-    const float PI = RT_PI;
-    if (cls == RT_CLASS_LAMBERT) {
-      dir = sample_hemisphere(n, ball);
-      brdf = albedo / PI;
-      pdf = 1.0f / (2.0f * PI);
-    } else if (cls == RT_CLASS_METAL) {
-      dir = reflectv(d, n) + roughness * ball;
-      brdf = albedo;
-      pdf = 1.0f;
-    } else if (cls == RT_CLASS_DIELECTRIC) {
-      float ior = roughness;  // stored in the roughness slot
-      float eta = front ? 1.0f / ior : ior;
-      float cth = fminf(-dot(d, n), 1.0f);
-      bool critical = eta * sqrtf(1.0f - cth * cth) > 1.0f;
-      float fres = fresnelf(d, n, ior);
-      bool will_refract = !critical && u_choice >= fres;
-      dir = will_refract ? refractv(d, n, eta) : reflectv(d, n);
-      brdf = mk(1.0f, 1.0f, 1.0f);
-      pdf = 1.0f;
-    } else if (cls == RT_CLASS_ISOTROPIC) {
-      dir = ball;
-      brdf = albedo;
-      pdf = 1.0f;
-    } else {  // PARAM / PARAM_TEX, materials.rs:114-145
-      float fres = fresnelf(d, n, 1.5f);
-      float k_s = fres * (1.0f - roughness);
-      float k_d = (1.0f - k_s) * (1.0f - metallic);
-      if (u_choice < k_d) {
-        dir = sample_hemisphere(n, ball);
-        brdf = albedo / PI;
-        pdf = 1.0f / (2.0f * PI);
-      } else {
-        dir = reflectv(d, n) + roughness * ball;
-        brdf = (1.0f - metallic) * mk(1.0f, 1.0f, 1.0f) + metallic * albedo;  // lerpvec(1, albedo, metallic)
-        pdf = 1.0f;
-      }
-    }
-    // tracing.rs:313-316
-    float dot_term = mag2(n) > 0.0f ? clampf(fabsf(dot(dir, n)), 0.0f, 1.0f) : 1.0f;
-    f3 w = (dot_term * brdf) / pdf;
-    nT = mulv(T, w);
-    if (MULTI) nT = nT / (float)fr.path_samples;
-    no = hp;
-    nd = dir;
-    bounce += 1;
-    sb = sample | (bounce << 24);
-    // the next segment exists only below path_depth (tracing.rs:301); a path whose throughput is
-    // exactly zero can add nothing any more
-    alive = bounce < fr.path_depth && !(nT.x == 0.0f && nT.y == 0.0f && nT.z == 0.0f);
+    alive = shade_hit<COUNT, MULTI>(sc, fr, p, best, cls, accum, ctrl->counters);
+    no = p.o; nd = p.d; nT = p.T;
+    pixel = p.pixel; sb = p.sb; tree = p.tree;
   }
 
   // compact survivors into the next ray queue, one atomic per block.  Inside the block's output range the rays are
@@ -458,6 +390,159 @@ __global__ void __launch_bounds__(RT_BLOCK, RT_SHADE_MIN_BLOCKS) k_shade(rt_dev_
       uint32_t peers = __match_any_sync(__activemask(), key);
       if ((peers & ((1u << lane) - 1u)) == 0) atomicAdd(&sort.hist[key], (uint32_t)__popc(peers));
     }
+  }
+}
+
+// ------------------------------------------------------------------ k_path (megakernel engine)
+// One persistent thread per path: the whole of Scene::shade_ray's recursion (tracing.rs:300-324) runs in place.
+// A lane generates its camera ray (Camera::generate_rays, tracing.rs:159-209), finds the closest hit with the same
+// traversal code as k_trace, shades it with the same shade_hit() as k_shade, and loops with the scattered ray; when
+// its path ends it claims the next work index and starts over ("path regeneration").  Nothing but the lowered scene
+// is read from HBM and nothing but the accumulator is written: the 148 bytes of queue state per path and six of the
+// wavefront engine's seven kernels per bounce are gone.  The price is that the 32 lanes of a warp hold paths at
+// different depths, so a warp's rays are less coherent than a sorted wavefront batch.
+//
+// The ray and the path's bookkeeping (throughput, pixel, sample | bounce) wait in shared memory while the lane
+// traverses, in the layout of the wavefront's ray queue (A, B, C quads), so the traversal code re-reads the world
+// ray and the RNG coordinates through the same pointers it uses there.  Images are bit-identical to the wavefront
+// engine's: same functions, same Philox keys, integer accumulation.
+#ifndef RT_PATH_MIN_BLOCKS
+#define RT_PATH_MIN_BLOCKS 6
+#endif
+#ifndef RT_PATH_REGEN_MIN
+#define RT_PATH_REGEN_MIN 1   // idle lanes that trigger a regeneration round (an all-idle warp always regenerates)
+#endif
+#ifndef RT_PATH_CHUNK_MAX
+#define RT_PATH_CHUNK_MAX 256  // work indices a warp claims per global atomic (guided: shrinks towards the end of the shard)
+#endif
+
+template <bool VOLMESH>
+__global__ void __launch_bounds__(RT_BLOCK, RT_PATH_MIN_BLOCKS) k_path(rt_dev_scene sc, rt_frame fr, rt_ctrl* __restrict__ ctrl,
+                                                                       long long* __restrict__ accum) {
+  __shared__ __align__(16) uint32_t sstack[(RT_SMEM_STACK + 6 + (VOLMESH ? 6 : 0)) * RT_BLOCK];
+  __shared__ float4 sA[RT_BLOCK], sB[RT_BLOCK], sC[RT_BLOCK];
+#if RT_TLAS_SMEM
+  __shared__ float4 s_tlas[RT_TLAS_SMEM * RT_NODE_QUADS];
+  load_tlas_cache(sc, s_tlas);
+#endif
+  const uint32_t tid = threadIdx.x, lane = tid & 31u;
+  const uint32_t FULL = 0xFFFFFFFFu;
+  uint32_t lstack[RT_LOCAL_STACK];
+  Trav T;
+  T.sbase = (uint32_t)__cvta_generic_to_shared(sstack) + tid * 4u;
+  T.wbase = (uint32_t)__cvta_generic_to_shared(sstack) + RT_SMEM_STACK * (RT_BLOCK * 4u) + tid * 4u;
+  T.lstack = lstack;
+#if RT_TLAS_SMEM
+  T.tbase = (uint32_t)__cvta_generic_to_shared(s_tlas);
+#endif
+  T.t_min = fr.t_min; T.t_max = fr.t_max;
+  T.k0 = fr.k0; T.k1 = fr.k1;
+  T.qA = sA; T.qB = sB; T.qC = sC;
+  T.slot = tid;
+  const unsigned long long total = ctrl->total;
+  const unsigned long long claimers = 4ull * gridDim.x * RT_WARPS;
+  bool have = false;
+  unsigned long long c_base = 0;       // this warp's claimed chunk of work indices (warp uniform)
+  uint32_t c_off = 0, c_cnt = 0;
+  bool exhausted = false;              // the shard has no more chunks (warp uniform)
+  uint32_t n_rays = 0, n_started = 0, n_invalid = 0;
+
+  for (;;) {
+    // ---- regeneration: idle lanes start the next camera paths of this warp's chunk
+    uint32_t need = __ballot_sync(FULL, !have);
+    if (need == FULL || __popc(need) >= RT_PATH_REGEN_MIN) {
+#pragma unroll 1
+      for (int round = 0; round < 2 && need; ++round) {
+        if (c_off >= c_cnt) {
+          if (exhausted) break;
+          unsigned long long base = 0;
+          uint32_t cnt = 0;
+          if (lane == 0) {
+            // guided self-scheduling: large chunks while there is plenty of work, 32 at the end (load balance of the tail)
+            unsigned long long cur = *reinterpret_cast<volatile unsigned long long*>(&ctrl->cursor);
+            unsigned long long want = cur < total ? (total - cur) / claimers : 0ull;
+            cnt = want >= RT_PATH_CHUNK_MAX ? (uint32_t)RT_PATH_CHUNK_MAX : (want < 32ull ? 32u : ((uint32_t)want & ~31u));
+            base = atomicAdd(&ctrl->cursor, (unsigned long long)cnt);
+          }
+          base = __shfl_sync(FULL, base, 0);
+          cnt = __shfl_sync(FULL, cnt, 0);
+          if (base >= total) {
+            exhausted = true;
+            break;
+          }
+          unsigned long long left = total - base;
+          c_base = base;
+          c_off = 0;
+          c_cnt = left < (unsigned long long)cnt ? (uint32_t)left : cnt;
+        }
+        const uint32_t avail = c_cnt - c_off;
+        const uint32_t rank = __popc(need & ((1u << lane) - 1u));
+        if (!have && rank < avail) {
+          uint32_t x, y, sample;
+          if (work_to_pixel(fr, c_base + c_off + rank, x, y, sample)) {
+            uint32_t pixel = y * fr.width + x;
+            f3 o, d;
+            camera_ray(fr, x, y, pixel, sample, o, d);
+            sA[tid] = make_float4(o.x, o.y, o.z, d.x);
+            sB[tid] = make_float4(d.y, d.z, 1.0f, 1.0f);
+            sC[tid] = make_float4(1.0f, __uint_as_float(pixel), __uint_as_float(sample), 0.0f);  // bounce 0
+            have = true;
+            ++n_started;
+          } else {
+            ++n_invalid;  // tile slot outside the image: the index is spent, the lane asks again
+          }
+        }
+        c_off += min((uint32_t)__popc(need), avail);
+        need = __ballot_sync(FULL, !have);
+      }
+    }
+    if (!__any_sync(FULL, have)) {
+      if (exhausted && c_off >= c_cnt) break;
+      continue;
+    }
+
+    // ---- closest hit (Scene::intersect_ray, tracing.rs:327-346)
+    bool fin = true;
+    if (have) {
+      float4 a = sA[tid], b = sB[tid];
+      T.t_max = T.ray_t_max = fr.t_max;
+      trav_begin<false>(sc, T, mk(a.x, a.y, a.z), mk(a.w, b.x, b.y));
+      fin = false;
+      ++n_rays;
+    }
+    while (!fin) fin = trav_round<false, VOLMESH>(sc, T, fr.t_min, T.ray_t_max);
+    __syncwarp();
+
+    // ---- shade and scatter (tracing.rs:305-322); a miss is the black background (tracing.rs:302-303)
+    if (have) {
+      if (T.best.obj < 0) {
+        have = false;
+      } else {
+        float4 a = sA[tid], b = sB[tid], c = sC[tid];
+        PathState p;
+        p.o = mk(a.x, a.y, a.z);
+        p.d = mk(a.w, b.x, b.y);
+        p.T = mk(b.z, b.w, c.x);
+        p.pixel = fbits(c.y);
+        p.sb = fbits(c.z);
+        p.tree = 0u;
+        have = shade_hit<false, false>(sc, fr, p, T.best, -1, accum, ctrl->counters);
+        if (have) {
+          sA[tid] = make_float4(p.o.x, p.o.y, p.o.z, p.d.x);
+          sB[tid] = make_float4(p.d.y, p.d.z, p.T.x, p.T.y);
+          sC[tid] = make_float4(p.T.z, __uint_as_float(p.pixel), __uint_as_float(p.sb), 0.0f);
+        }
+      }
+    }
+  }
+  // ---- bookkeeping: one atomic per warp and counter
+  n_rays = __reduce_add_sync(FULL, n_rays);
+  n_started = __reduce_add_sync(FULL, n_started);
+  n_invalid = __reduce_add_sync(FULL, n_invalid);
+  if (lane == 0) {
+    atomicAdd(&ctrl->n_rays_total, (unsigned long long)n_rays);
+    atomicAdd(&ctrl->n_samples, (unsigned long long)(n_started + n_invalid));
+    if (n_invalid) atomicAdd(&ctrl->counters[7], (unsigned long long)n_invalid);
   }
 }
 
@@ -712,6 +797,19 @@ int trace_blocks_per_sm() {
   int n = 0;
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_trace<false, false>, RT_BLOCK, 0);
   return n > 0 ? n : 1;
+}
+int path_blocks_per_sm() {
+  int n = 0;
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_path<false>, RT_BLOCK, 0);
+  return n > 0 ? n : 1;
+}
+void launch_path(const rt_dev_scene& sc, const rt_frame& fr, rt_ctrl* ctrl, long long* accum, unsigned long long total,
+                 uint32_t persistent_blocks, cudaStream_t st) {
+  unsigned long long full = (total + RT_BLOCK - 1) / RT_BLOCK;
+  uint32_t grid = (uint32_t)(full < persistent_blocks ? full : persistent_blocks);
+  if (grid == 0) return;
+  if (sc.n_volume_meshes) k_path<true><<<grid, RT_BLOCK, 0, st>>>(sc, fr, ctrl, accum);
+  else k_path<false><<<grid, RT_BLOCK, 0, st>>>(sc, fr, ctrl, accum);
 }
 void launch_raygen(const rt_frame& fr, rt_ctrl* ctrl, rt_paths cur, cudaStream_t st) {
   k_raygen<<<(fr.capacity + RT_BLOCK - 1) / RT_BLOCK, RT_BLOCK, 0, st>>>(fr, ctrl, cur);

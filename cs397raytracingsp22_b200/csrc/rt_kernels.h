@@ -46,6 +46,10 @@ void launch_sort(const rt_dev_scene& sc, const rt_frame& fr, rt_ctrl* ctrl, rt_h
 void launch_surface(const rt_dev_scene& sc, const rt_frame& fr, rt_ctrl* ctrl, rt_paths cur, rt_hits hits, rt_debug dbg,
                     cudaStream_t st);
 int trace_blocks_per_sm();
+// megakernel engine: one persistent kernel renders work indices [ctrl->cursor, ctrl->total) into the accumulator
+int path_blocks_per_sm();
+void launch_path(const rt_dev_scene& sc, const rt_frame& fr, rt_ctrl* ctrl, long long* accum, unsigned long long total,
+                 uint32_t persistent_blocks, cudaStream_t st);
 void launch_shade(const rt_dev_scene& sc, const rt_frame& fr, rt_ctrl* ctrl, rt_paths cur, rt_paths nxt, rt_hits hits,
                   const uint32_t* queues, long long* accum, rt_sortbuf sort, bool count, cudaStream_t st);
 void launch_set_window(rt_ctrl* ctrl, uint32_t n_cont, uint32_t n_new, cudaStream_t st);

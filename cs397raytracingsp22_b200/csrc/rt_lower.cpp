@@ -101,19 +101,22 @@ inline float half_area(const float* mn, const float* mx) {
   return ex * ey + ey * ez + ez * ex;
 }
 
-// tuning knobs (development): RT_LEAF_MAX (1..8), RT_SAH_CT (cost of a node-pair visit in triangle tests)
-float g_sah_ct = 1.0f;
-uint32_t g_leaf_max = 4;
-int g_sweep = 1;  // 1: full-sweep SAH (every split position on every axis) instead of 16 bins
+// builder settings, compile-time (each was measured on the device, profiles/r1_notes.md: leaf size 2 / 4 / 8 and
+// traversal cost 0.5 / 1 / 2 move the frame time by < 1 %; the full sweep beats 16 bins by 0.6 %)
+#ifndef RT_LEAF_MAX
+#define RT_LEAF_MAX 4      // triangles per BLAS leaf, 1..RT_MAX_LEAF_TRIS
+#endif
+#ifndef RT_SAH_CT
+#define RT_SAH_CT 1.0f     // cost of a node-pair visit in triangle tests
+#endif
+#ifndef RT_SAH_SWEEP
+#define RT_SAH_SWEEP 1     // 1: full-sweep SAH (every split position on every axis), 0: 16 bins
+#endif
+static_assert(RT_LEAF_MAX >= 1 && RT_LEAF_MAX <= RT_MAX_LEAF_TRIS, "leaf size must fit the packed entry");
+const float g_sah_ct = RT_SAH_CT;
+const uint32_t g_leaf_max = RT_LEAF_MAX;
+const int g_sweep = RT_SAH_SWEEP;
 float g_prim_cost = 1.0f;       // set per build
-void read_knobs() {
-  static bool done = false;
-  if (done) return;
-  done = true;
-  if (const char* e = std::getenv("RT_LEAF_MAX")) g_leaf_max = (uint32_t)std::min(RT_MAX_LEAF_TRIS, std::max(1, std::atoi(e)));
-  if (const char* e = std::getenv("RT_SAH_CT")) g_sah_ct = (float)std::atof(e);
-  if (const char* e = std::getenv("RT_SAH_SWEEP")) g_sweep = std::atoi(e);
-}
 
 // full-sweep SAH: best (axis, position) over all count-1 splits of the centroid-sorted order.
 // On success prims[first, first+count) is sorted along the best axis and `mid` is the split index.
@@ -333,6 +336,28 @@ uint32_t bvh_depth(const std::vector<BNode>& nodes, uint32_t ni = 0) {
   return 1 + std::max(bvh_depth(nodes, nodes[ni].leftFirst), bvh_depth(nodes, nodes[ni].leftFirst + 1));
 }
 
+// breadth-first order (root, padding, then child pairs level by level): the first N nodes are the top of the tree,
+// which is what a kernel wants to keep in shared memory
+void reorder_bfs(std::vector<BNode>& nodes) {
+  if (nodes.size() <= 2) return;
+  std::vector<BNode> out;
+  out.reserve(nodes.size());
+  out.push_back(nodes[0]);
+  out.push_back(nodes[1]);
+  std::vector<uint32_t> queue{0};  // indices into `out` of nodes whose children still have to be placed
+  for (size_t qi = 0; qi < queue.size(); ++qi) {
+    uint32_t ni = queue[qi];
+    if (out[ni].count) continue;
+    uint32_t old_left = out[ni].leftFirst, new_left = (uint32_t)out.size();
+    out.push_back(nodes[old_left]);
+    out.push_back(nodes[old_left + 1]);
+    out[ni].leftFirst = new_left;
+    queue.push_back(new_left);
+    queue.push_back(new_left + 1);
+  }
+  nodes.swap(out);
+}
+
 inline uint32_t pack_entry(uint32_t leftFirst, uint32_t count) {
   return count ? (RT_LEAF_FLAG | (leftFirst << 4) | count) : leftFirst;
 }
@@ -420,7 +445,6 @@ void build_mesh(HostMesh& m) {
   m.n_reachable = (uint32_t)prims.size();
 
   std::vector<BNode> nodes;
-  read_knobs();
   g_prim_cost = 1.0f;
   build_bvh(prims, g_leaf_max, nodes);
   // Conservative traversal: boxes are padded by a few ulps of the largest coordinate so that a
@@ -725,9 +749,10 @@ int lower_scene(const std::vector<HostTexture>& textures, const std::vector<rt_m
       bool finite = true;
       for (int k = 0; k < 3; ++k) finite = finite && std::isfinite(p.mn[k]) && std::isfinite(p.mx[k]);
       if (!finite) {
-        // cannot be bounded (e.g. NaN transform): test it for every ray instead
-        if (o.kind != RT_OBJ_MESH && o.kind != RT_OBJ_VOLUME_MESH) L.planes.push_back((int32_t)oi);
-        continue;
+        // NaN / infinite centre, radius, vertex or transform: such an object cannot be bounded, and the always-tested
+        // list only knows planes.  Refused loudly rather than silently never intersected.
+        err = "object " + std::to_string(oi) + " has non-finite coordinates (it cannot be placed in the TLAS)";
+        return RT_ERR_UNSUPPORTED;
       }
       float amax = 0.0f;
       for (int k = 0; k < 3; ++k) amax = std::max(amax, std::max(std::fabs(p.mn[k]), std::fabs(p.mx[k])));
@@ -755,10 +780,10 @@ int lower_scene(const std::vector<HostTexture>& textures, const std::vector<rt_m
   // TLAS: one object per leaf, the leaf's link holds the object index directly.  (Measured: leaves of 2-8 analytic
   // objects behind an index list cut TLAS node visits from 9.8 to 9.0 per ray but were 1-2 % slower.)
   if (!tprims.empty()) {
-    read_knobs();
     g_prim_cost = 1.0f;
     std::vector<BNode> tn;
     build_bvh(tprims, 1, tn);
+    reorder_bfs(tn);
     L.tlas_depth = bvh_depth(tn);
     for (auto& n : tn)
       if (n.count) n.leftFirst = tprims[n.leftFirst].id;  // leaf -> object index
@@ -768,6 +793,8 @@ int lower_scene(const std::vector<HostTexture>& textures, const std::vector<rt_m
     for (size_t q = 0; q < tq.size(); q += 2)
       if (tq[q + 1].u[3] == 0) tq[q].u[3] += base;
     L.nodes.insert(L.nodes.end(), tq.begin(), tq.end());
+    L.tlas_base = base;
+    L.tlas_count = (uint32_t)tn.size();
     L.tlas_root = tn[0].count ? pack_entry(tn[0].leftFirst, tn[0].count) : (tn[0].leftFirst + base);
     for (int k = 0; k < 3; ++k) {
       L.tlas_min[k] = tn[0].mn[k];

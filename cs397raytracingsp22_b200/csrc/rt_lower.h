@@ -64,6 +64,7 @@ struct Lowered {
   std::vector<Quad> guards;
   std::vector<uint32_t> guard_list;
   uint32_t tlas_root = RT_ENTRY_NONE;
+  uint32_t tlas_base = 0, tlas_count = 0;  // where the TLAS nodes sit in `nodes` (breadth-first order)
   float tlas_min[3] = {0, 0, 0}, tlas_max[3] = {0, 0, 0};
   uint32_t n_volumes = 0;
   uint32_t tlas_depth = 0;

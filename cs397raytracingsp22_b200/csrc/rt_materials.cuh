@@ -71,7 +71,11 @@ __device__ __forceinline__ uint32_t ray_sort_key(const rt_frame& fr, f3 o, f3 d)
   return (h << 3) | (fr.sort_use_octant ? oct : 0u);
 }
 
-// fixed-point accumulation (2^-30 units): order-independent, hence reproducible and shardable
+// fixed-point accumulation (2^-30 units): order-independent, hence reproducible and shardable.
+// Headroom: a sample is clamped to +-65536 = 2^46 units, so a pixel's int64 sum is exact for up to 2^17 samples that
+// sit AT the clamp (radiance 65536), i.e. for any realistic image with aa_sample_count * ranks < 2^24.  A NaN sample sets
+// a sticky bit per channel in the fourth word (bit 21*k; bits, not counts, so no number of NaN samples can carry into
+// the neighbouring channel or wrap to zero; summing the words of up to 2^21 ranks keeps the fields apart).
 #define RT_FIX_SCALE 1073741824.0f
 #define RT_FIX_CLAMP 65536.0f
 __device__ __forceinline__ void accum_add(long long* accum, uint32_t pixel, f3 c) {
@@ -80,7 +84,7 @@ __device__ __forceinline__ void accum_add(long long* accum, uint32_t pixel, f3 c
   for (int k = 0; k < 3; ++k) {
     float x = v[k];
     if (x != x) {
-      atomicAdd(reinterpret_cast<unsigned long long*>(accum + (size_t)pixel * 4 + 3), 1ull << (21 * k));
+      atomicOr(reinterpret_cast<unsigned long long*>(accum + (size_t)pixel * 4 + 3), 1ull << (21 * k));
     } else if (x != 0.0f) {
       x = fminf(fmaxf(x, -RT_FIX_CLAMP), RT_FIX_CLAMP);
       long long q = __float2ll_rn(x * RT_FIX_SCALE);

@@ -70,10 +70,11 @@ const uint16_t LEXT[29] = {0, 0, 0, 0, 0, 0, 0, 0, 1, 1, 1, 1, 2, 2, 2, 2, 3, 3,
 const uint16_t DBASE[30] = {1, 2, 3, 4, 5, 7, 9, 13, 17, 25, 33, 49, 65, 97, 129, 193, 257, 385, 513, 769, 1025, 1537, 2049, 3073, 4097, 6145, 8193, 12289, 16385, 24577};
 const uint16_t DEXT[30] = {0, 0, 0, 0, 1, 1, 2, 2, 3, 3, 4, 4, 5, 5, 6, 6, 7, 7, 8, 8, 9, 9, 10, 10, 11, 11, 12, 12, 13, 13};
 
-bool inflate_codes(BitReader& br, std::vector<uint8_t>& out, const Huffman& lc, const Huffman& dc) {
+bool inflate_codes(BitReader& br, std::vector<uint8_t>& out, const Huffman& lc, const Huffman& dc, size_t max_out) {
   for (;;) {
     int sym = lc.decode(br);
     if (sym < 0) return false;
+    if (out.size() > max_out) return false;  // more data than the image can hold: refuse (zip bomb)
     if (sym < 256) {
       out.push_back((uint8_t)sym);
     } else if (sym == 256) {
@@ -92,7 +93,8 @@ bool inflate_codes(BitReader& br, std::vector<uint8_t>& out, const Huffman& lc, 
   }
 }
 
-bool inflate(const uint8_t* src, size_t n, std::vector<uint8_t>& out) {
+// `max_out`: the caller knows how many bytes the stream may legitimately produce; anything beyond that is refused
+bool inflate(const uint8_t* src, size_t n, std::vector<uint8_t>& out, size_t max_out) {
   BitReader br{src, n};
   int last;
   do {
@@ -105,7 +107,7 @@ bool inflate(const uint8_t* src, size_t n, std::vector<uint8_t>& out) {
       if (br.pos + 4 > n) return false;
       uint32_t len = src[br.pos] | (src[br.pos + 1] << 8), nlen = src[br.pos + 2] | (src[br.pos + 3] << 8);
       br.pos += 4;
-      if ((len ^ 0xFFFFu) != nlen || br.pos + len > n) return false;
+      if ((len ^ 0xFFFFu) != nlen || br.pos + len > n || out.size() + len > max_out + 258) return false;
       out.insert(out.end(), src + br.pos, src + br.pos + len);
       br.pos += len;
     } else if (type == 1) {
@@ -119,7 +121,7 @@ bool inflate(const uint8_t* src, size_t n, std::vector<uint8_t>& out) {
       uint8_t d[30];
       for (int i = 0; i < 30; ++i) d[i] = 5;
       dc.build(d, 30);
-      if (!inflate_codes(br, out, lc, dc)) return false;
+      if (!inflate_codes(br, out, lc, dc, max_out)) return false;
     } else if (type == 2) {
       int nlen = br.bits(5) + 257, ndist = br.bits(5) + 1, ncode = br.bits(4) + 4;
       if (br.fail || nlen > 286 || ndist > 30) return false;
@@ -156,7 +158,7 @@ bool inflate(const uint8_t* src, size_t n, std::vector<uint8_t>& out) {
       Huffman lc, dc;
       lc.build(ll, nlen);
       dc.build(ll + nlen, ndist);
-      if (!inflate_codes(br, out, lc, dc)) return false;
+      if (!inflate_codes(br, out, lc, dc, max_out)) return false;
     } else {
       return false;
     }
@@ -221,11 +223,15 @@ int png_decode(const uint8_t* b, size_t len, uint8_t** rgb, uint32_t* w, uint32_
     return RT_ERR_IO;
   }
   if (idat.size() < 6) { err = "PNG has no image data"; return RT_ERR_IO; }
-  std::vector<uint8_t> raw;
-  raw.reserve((size_t)H * ((size_t)W * channels * depth / 8 + 2));
-  if (!inflate(idat.data() + 2, idat.size() - 2, raw)) { err = "PNG inflate failed"; return RT_ERR_IO; }
   size_t bpp = std::max<size_t>(1, (size_t)channels * depth / 8);
   size_t stride = ((size_t)W * channels * depth + 7) / 8;
+  const size_t expected = (stride + 1) * (size_t)H;
+  // deflate expands by at most 1032:1, so a header that promises more pixels than the IDAT bytes can produce is
+  // refused before anything is allocated for it
+  if (expected / 1032 > idat.size()) { err = "PNG image data too short"; return RT_ERR_IO; }
+  std::vector<uint8_t> raw;
+  raw.reserve(expected + 258);
+  if (!inflate(idat.data() + 2, idat.size() - 2, raw, expected)) { err = "PNG inflate failed"; return RT_ERR_IO; }
   if (raw.size() < (stride + 1) * (size_t)H) { err = "PNG image data too short"; return RT_ERR_IO; }
   std::vector<uint8_t> prev(stride, 0), cur(stride);
   uint8_t* out = (uint8_t*)std::malloc((size_t)W * H * 3);

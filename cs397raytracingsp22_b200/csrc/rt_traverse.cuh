@@ -89,6 +89,9 @@ struct Trav {
   uint32_t vol_phase;  // mesh-bounded volume: 0 = none, 1 = entry query running, 2 = exit query running
   bool volret;         // pop_next just popped the end-of-query marker
   uint32_t* lstack;  // RT_LOCAL_STACK entries of local memory, declared by the kernel
+#if RT_TLAS_SMEM
+  uint32_t tbase;    // shared-space byte address of the block's copy of the top of the TLAS
+#endif
   Best best;
   Cnt cnt;
   uint32_t k0, k1;  // Philox key (kernel constants)
@@ -197,13 +200,42 @@ __device__ __noinline__ bool guards_pass(const rt_dev_scene& sc, uint32_t first,
   return true;
 }
 
+#if RT_TLAS_SMEM
+// Every ray starts at the top of the TLAS, so a persistent block keeps the first RT_TLAS_SMEM TLAS nodes (breadth-first
+// order: the top levels) in shared memory: those fetches never miss and leave L1 to the BLAS nodes.
+__device__ __forceinline__ uint32_t tlas_cached(const rt_dev_scene& sc) {
+  return sc.tlas_count < (uint32_t)RT_TLAS_SMEM ? sc.tlas_count : (uint32_t)RT_TLAS_SMEM;
+}
+__device__ __forceinline__ void load_tlas_cache(const rt_dev_scene& sc, float4* s_tlas) {
+  const uint32_t nq = tlas_cached(sc) * RT_NODE_QUADS;
+  const float4* src = reinterpret_cast<const float4*>(sc.nodes) + (size_t)sc.tlas_base * RT_NODE_QUADS;
+  for (uint32_t i = threadIdx.x; i < nq; i += blockDim.x) s_tlas[i] = __ldg(src + i);
+  __syncthreads();
+}
+__device__ __forceinline__ float4 lds_quad(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
+}
+#endif
+
 // interior node: fetch the 64-byte child pair with four 128-bit read-only loads, test both boxes,
 // continue with the nearer child and push the other
 template <bool COUNT>
 __device__ __forceinline__ void trav_interior(const rt_dev_scene& sc, Trav& T) {
   uint32_t e = T.entry;
-  const float4* pair = reinterpret_cast<const float4*>(sc.nodes) + (size_t)e * 2u;
-  float4 l0 = __ldg(pair), l1 = __ldg(pair + 1), r0 = __ldg(pair + 2), r1 = __ldg(pair + 3);
+  float4 l0, l1, r0, r1;
+#if RT_TLAS_SMEM
+  const uint32_t rel = e - sc.tlas_base;  // BLAS nodes lie below tlas_base: rel wraps to a huge value
+  if (rel < tlas_cached(sc)) {            // pairs never straddle the end: the cached count is even, like every pair index
+    const uint32_t a = T.tbase + rel * 32u;
+    l0 = lds_quad(a); l1 = lds_quad(a + 16u); r0 = lds_quad(a + 32u); r1 = lds_quad(a + 48u);
+  } else
+#endif
+  {
+    const float4* pair = reinterpret_cast<const float4*>(sc.nodes) + (size_t)e * 2u;
+    l0 = __ldg(pair); l1 = __ldg(pair + 1); r0 = __ldg(pair + 2); r1 = __ldg(pair + 3);
+  }
   if (COUNT) {
     T.cnt.nodes += 2;
     if (!T.in_blas) T.cnt.tlas_nodes += 2;
@@ -396,10 +428,7 @@ __device__ __forceinline__ void test_unbounded(const rt_dev_scene& sc, Trav& T, 
   }
 }
 
-// start the closest-hit query of the ray in T.wo / T.wd
-template <bool COUNT>
-__device__ __forceinline__ void test_unbounded(const rt_dev_scene& sc, Trav& T, f3 wo, f3 wd);
-
+// start the closest-hit query of the world-space ray (wo, wd)
 template <bool COUNT>
 __device__ __forceinline__ void trav_begin(const rt_dev_scene& sc, Trav& T, f3 wo, f3 wd) {
   T.set_space(wo, wd);
@@ -424,10 +453,6 @@ __device__ __forceinline__ void trav_begin(const rt_dev_scene& sc, Trav& T, f3 w
     if (!slab(lo, hi, T.inv, T.oi, T.t_min, T.best.t, tn)) T.entry = RT_ENTRY_NONE;
   }
 }
-// one round: descend while interior, then the leaf this lane reached (if any), then pop.
-// Returns true when the stack is exhausted.  (Measured on B200: postponing leaves until every lane
-// of the warp holds one - "while-while" - is 30 % slower here, because leaves are cheap (1.9
-// triangle tests per ray) compared with the descent they would make the other lanes wait for.)
 // A boundary query of a mesh-bounded volume has finished (its end marker was popped).  Phase 1 found t_entr: start
 // the exit query from t_entr + 1e-4 (geometry.rs:508).  Phase 2 found t_exit: the rest of ConvexVolume::intersect_ray
 // (geometry.rs:512-525) with the ray's own t-range, then back to the world-space traversal.

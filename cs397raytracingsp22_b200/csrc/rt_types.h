@@ -63,6 +63,8 @@ struct rt_dev_scene {
   const void* guards;    // float4* guard boxes (min, max)
   const void* guard_list;// uint32_t* per-triangle guard indices
   uint32_t tlas_root;    // packed entry of the TLAS root, RT_ENTRY_NONE when there is none
+  uint32_t tlas_base;    // node index of the first TLAS node (the TLAS is stored breadth first behind all BLASes)
+  uint32_t tlas_count;   // number of TLAS nodes (incl. the padding node 1)
   uint32_t n_planes;
   uint32_t n_objects;
   uint32_t n_volumes;

@@ -29,7 +29,8 @@ def tiles_of_rank(rank: int, world: int, width: int, height: int, tile: int = 64
 
 
 def shard_opts(rank: int, world: int, seed: int, mode: str = "samples", tile: int = 64, sample_begin: int = 0,
-               sample_end: int = 0, wavefront: int = 0, flags: int = 0) -> _ffi.rt_render_opts:
+               sample_end: int = 0, wavefront: int = 0, flags: int = 0, engine: int = 0, ray_sort: int = 0,
+               work_order: int = 0, blocks_per_sm: int = 0) -> _ffi.rt_render_opts:
     o = _ffi.rt_render_opts()
     o.seed = seed
     o.shard_mode = {"all": _ffi.RT_SHARD_ALL, "samples": _ffi.RT_SHARD_SAMPLES, "tiles": _ffi.RT_SHARD_TILES}[mode]
@@ -38,6 +39,7 @@ def shard_opts(rank: int, world: int, seed: int, mode: str = "samples", tile: in
     o.sample_begin, o.sample_end = sample_begin, sample_end
     o.wavefront = wavefront
     o.flags = flags
+    o.engine, o.ray_sort, o.work_order, o.blocks_per_sm = engine, ray_sort, work_order, blocks_per_sm
     return o
 
 

@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define RT_B200_ABI_VERSION 2
+#define RT_B200_ABI_VERSION 3
 
 typedef enum rt_status {
   RT_OK = 0,
@@ -94,6 +94,20 @@ enum {
   RT_OPT_NO_EVENTS = 1u << 1 /* do not bracket kernels with CUDA events               */
 };
 
+/* How the device walks the paths of one render call.  Both engines run the same device functions on the same
+ * Philox keys and add into the same integer accumulators, so their images are bit-identical.
+ *   WAVEFRONT : ray-gen / closest-hit / material-sorted shade kernels over a queue of paths in HBM
+ *   MEGAKERNEL: one persistent kernel, one thread per path, the path's state in registers and shared memory,
+ *               finished lanes start the next camera path at once
+ *   AUTO      : chosen per call (pick_engine() in csrc/rt_api.cu; measurements in DESIGN.md).  The debug modes of
+ *               the reference (ShadingMode::Phong, path_samples > 1) and the device counters exist in the
+ *               wavefront engine only and always select it. */
+enum { RT_ENGINE_AUTO = 0, RT_ENGINE_WAVEFRONT = 1, RT_ENGINE_MEGAKERNEL = 2 };
+/* wavefront engine only: sort the scattered rays by (origin cell, direction class) before the next closest-hit pass */
+enum { RT_RAYSORT_AUTO = 0, RT_RAYSORT_OFF = 1, RT_RAYSORT_ON = 2 };
+/* order in which work indices walk the shard: AUTO picks per shard mode */
+enum { RT_ORDER_AUTO = 0, RT_ORDER_PIXEL_MAJOR = 1, RT_ORDER_SAMPLE_MAJOR = 2, RT_ORDER_GROUPED = 3 };
+
 typedef struct rt_render_opts {
   uint64_t seed;          /* Philox key                                              */
   uint32_t shard_mode;    /* RT_SHARD_*                                              */
@@ -102,10 +116,15 @@ typedef struct rt_render_opts {
   uint32_t tile_size;     /* RT_SHARD_TILES: square tile edge in pixels (0 => 64)    */
   uint32_t sample_begin;  /* RT_SHARD_ALL/TILES: [begin,end) sample indices;         */
   uint32_t sample_end;    /*   both 0 => [0, aa_sample_count)                        */
-  uint32_t wavefront;     /* paths in flight (0 => library default)                  */
+  uint32_t wavefront;     /* wavefront engine: paths in flight (0 => library default) */
   uint32_t flags;         /* RT_OPT_*                                                */
   float point_light_pos[3]; /* Scene::point_light_pos, used by ShadingMode::Phong only (tracing.rs:216) */
   float ambient[3];         /* Scene::ambient, Phong only (tracing.rs:217)                              */
+  uint32_t engine;        /* RT_ENGINE_*  (0 => AUTO)                                */
+  uint32_t ray_sort;      /* RT_RAYSORT_* (0 => AUTO: on when the instanced triangle count is >= 16 Ki) */
+  uint32_t work_order;    /* RT_ORDER_*   (0 => AUTO)                                */
+  uint32_t blocks_per_sm; /* resident blocks per SM of the persistent kernels (0 => what the occupancy query says) */
+  uint32_t reserved[4];   /* must be 0                                               */
 } rt_render_opts;
 
 typedef struct rt_stats {
@@ -204,7 +223,7 @@ int rt_render(rt_scene* s, const rt_camera* cam, const rt_render_opts* opts,
 
 /* Device-resident pieces of the same call, for one-process-per-GPU sharding.
  * d_accum is a DEVICE pointer to W*H*4 int64: fixed-point (2^-30) radiance sums for
- * R,G,B and a packed NaN counter; rt_render_accum ADDS this shard's samples into it
+ * R,G,B and a word of per-channel NaN flags; rt_render_accum ADDS this shard's samples into it
  * (zero it first).  Because the sums are integers they are exact and independent of
  * order, so summing shards (e.g. with an NCCL int64 all-reduce) is bit-identical to
  * one GPU rendering everything.  `stream` is a cudaStream_t (0 => default stream). */

@@ -21,14 +21,14 @@ def test_library_exports_every_declared_symbol(rtlib):
     for name in sorted(declared):
         assert hasattr(rtlib, name), f"librt_b200.so does not export {name}"
     assert declared == set(_ffi.SIGNATURES), "ctypes table and header disagree"
-    assert rtlib.rt_abi_version() == _ffi.RT_B200_ABI_VERSION == 2
+    assert rtlib.rt_abi_version() == _ffi.RT_B200_ABI_VERSION == 3
 
 
 def test_struct_layouts_match_the_header():
     # sizes the C side static-asserts implicitly through use; a drift here corrupts every call
     assert C.sizeof(_ffi.rt_material_desc) == 40
     assert C.sizeof(_ffi.rt_camera) == 84
-    assert C.sizeof(_ffi.rt_render_opts) == 64
+    assert C.sizeof(_ffi.rt_render_opts) == 96
     assert C.sizeof(_ffi.rt_stats) == 16 * 8 + 4 * 8 + 2 * 8
 
 
