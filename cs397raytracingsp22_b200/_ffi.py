@@ -64,7 +64,7 @@ class rt_stats(C.Structure):
         "tris_tested", "instances_entered", "prims_tested", "mesh_hits", "texel_taps", "extend_texel_taps",
         "material_fetches", "warp_node_slots")] + [
         (n, C.c_double) for n in ("ms_total", "ms_extend", "ms_shade", "ms_resolve")] + [
-        ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64)]
+        ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64), ("engine", C.c_uint64)]
 
     def as_dict(self) -> dict:
         return {n: getattr(self, n) for n, _ in self._fields_}

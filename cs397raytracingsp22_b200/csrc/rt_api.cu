@@ -429,6 +429,7 @@ int run_wavefront(rt_scene* s, const rt_frame& fr_in, unsigned long long total, 
     cudaEventElapsedTime(&ms, ev_begin, ev_end);
     stats->ms_total += ms;
     stats_from_ctrl(c, stats);
+    stats->engine = RT_ENGINE_WAVEFRONT;
     stats->iterations += c.iterations;
     stats->kernel_launches += launches;
     // report the launches that did work, not the no-op tail queued behind the `done` poll
@@ -482,6 +483,7 @@ int run_megakernel(rt_scene* s, const rt_frame& fr_in, unsigned long long total,
     cudaEventElapsedTime(&ms, ev.a, ev.b);
     stats->ms_total += ms;
     stats->ms_extend += ms;  // closest hit and shading are one kernel here
+    stats->engine = RT_ENGINE_MEGAKERNEL;
     stats_from_ctrl(c, stats);
     stats->iterations += 1;
     stats->kernel_launches += 2;
@@ -569,6 +571,7 @@ int run_branching(rt_scene* s, const rt_frame& fr_in, unsigned long long total, 
     stats->ms_total += ms;
     stats->samples += c.n_samples - c.counters[7];
     stats->rays += c.n_rays_total - c.counters[7];
+    stats->engine = RT_ENGINE_WAVEFRONT;
     stats->iterations += iters;
     stats->kernel_launches += launches;
     stats->extend_launches += iters;
@@ -808,6 +811,8 @@ int rt_scene_upload(rt_scene* s) try {
   d.nodes = s->d_nodes.p; d.tris = s->d_tris.p; d.shade = s->d_shade.p; d.objects = s->d_objects.p;
   d.mats = s->d_mats.p; d.textures = s->d_textures.p; d.texels = s->d_texels.p; d.planes = s->d_planes.p; d.guards = s->d_guards.p; d.guard_list = s->d_guard_list.p;
   d.tlas_root = L.tlas_root;
+  d.tlas_base = L.tlas_base;
+  d.tlas_count = L.tlas_count & ~1u;  // whole child pairs
   d.n_planes = (L.planes.size() == 1 && L.planes[0] < 0) ? 0u : (uint32_t)L.planes.size();
   d.n_objects = (uint32_t)s->objects.size();
   d.n_volumes = L.n_volumes;

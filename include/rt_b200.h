@@ -153,6 +153,7 @@ typedef struct rt_stats {
   double ms_resolve;
   uint64_t h2d_bytes;         /* bytes copied host->device by this call             */
   uint64_t d2h_bytes;         /* bytes copied device->host by this call             */
+  uint64_t engine;            /* RT_ENGINE_* that rendered this call (never AUTO)    */
 } rt_stats;
 
 typedef struct rt_scene rt_scene; /* opaque, library-owned: replaces `Scene.objects` (tracing.rs:215) */

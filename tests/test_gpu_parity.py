@@ -160,7 +160,7 @@ def _render_pair(sc, spp_kw=None):
     return lin_g, rgb_g, st_g, lin_o, rgb_o, st_o
 
 
-@pytest.mark.parametrize("name", ["c1", "c2", "c3", "c4"])
+@pytest.mark.parametrize("name", ["c1", "c2", "c3", "c4", "c5"])
 def test_low_spp_images_track_the_oracle_sample_for_sample(gpu, small_scenes, name):
     """Same Philox keys on both sides: at 16 spp the two images must agree far below Monte-Carlo noise.  A path only
     decorrelates when an ulp-level difference (libm sin/cos/cbrt/log, summation order) flips a discrete decision."""
@@ -182,7 +182,10 @@ def test_low_spp_images_track_the_oracle_sample_for_sample(gpu, small_scenes, na
 
 
 @pytest.mark.parametrize("name,kw", [("c1", dict(width=48, height=48, spp=1024)),
-                                     ("c4", dict(width=64, height=36, spp=1024, map_size=256))])
+                                     ("c2", dict(width=48, height=48, spp=1024)),
+                                     ("c3", dict(width=48, height=48, spp=1024)),
+                                     ("c4", dict(width=64, height=36, spp=1024, map_size=256)),
+                                     ("c5", dict(width=64, height=36, spp=1024, map_size=128, grid=6))])
 def test_converged_images_rmse(gpu, small_scenes, name, kw):
     """>= 1024 spp, reduced resolution (so the CPU side takes seconds): RMSE in linear radiance, relative to the mean
     radiance, must be < 0.5 % and PSNR (peak = 1.0) > 50 dB; the u8 images agree within 1 LSB on > 99 % of pixels."""
@@ -586,6 +589,108 @@ def test_full_resolution_c4_properties(gpu):
     b = o.trace_primary(cam, SEED, 777, mode=O.MODE_REF_TREE)
     assert np.array_equal(a["ray"], b["ray"])
     _assert_hits_match(a, b, "c4 full resolution", _volume_ids(sc))
+
+
+def _full_size_checks(name, expect, sample_window, shards, prim_sample, prim_stride=1):
+    """Shared body of the full-size property tests: the frame (or a window of its sample indices) is rendered by both
+    engines and in shards - all accumulators bit-identical; the checksum of per-row checksums equals the total; ray
+    counts obey samples <= rays <= samples * depth; one sample index of primary hits agrees with the reference-tree
+    oracle (every `prim_stride`-th pixel; with defocus the oracle is asked about the GPU's own camera rays, which
+    differ from its own by an ulp of sin/cos)."""
+    import torch
+    from cs397raytracingsp22_b200 import scenes
+    sc = scenes.make_scene(name)
+    g, o = _both(sc)
+    cam = sc.camera.to_c()
+    w, h, spp, depth = cam.screen_width, cam.screen_height, cam.aa_sample_count, cam.path_depth
+    assert (w, h, spp, depth) == expect
+    lo, hi = sample_window
+    dev = torch.device("cuda", 0)
+
+    def run(opts_list):
+        acc = D.new_accum(w, h, dev)
+        stats = [D.render_shard(g, cam, op, acc) for op in opts_list]
+        torch.cuda.synchronize()
+        return acc, stats
+
+    win = dict(sample_begin=lo, sample_end=hi)
+    full, st = run([D.shard_opts(0, 1, SEED, "all", engine=_ffi.RT_ENGINE_WAVEFRONT, **win)])
+    assert st[0].samples == w * h * (hi - lo)
+    assert st[0].samples <= st[0].rays <= st[0].samples * depth
+    mega, stm = run([D.shard_opts(0, 1, SEED, "all", engine=_ffi.RT_ENGINE_MEGAKERNEL, **win)])
+    assert torch.equal(full, mega) and stm[0].rays == st[0].rays
+    for mode, world, kw in shards:
+        parts, sts = run([D.shard_opts(r, world, SEED, mode, **win, **kw) for r in range(world)])
+        assert torch.equal(full, parts), (mode, world)
+        assert sum(s.samples for s in sts) == w * h * (hi - lo)
+    a = full.view(h, w, 4)
+    assert torch.equal(a.sum(dim=1).sum(dim=0), a.sum(dim=(0, 1)))
+    assert int(a[..., 3].abs().sum()) == 0                                  # no NaN samples
+    assert int((a[..., :3].sum(dim=2) > 0).sum()) > 0.5 * w * h             # the frame is lit
+    pg = g.trace_primary(cam, SEED, prim_sample)
+    if cam.lens_radius == 0.0 and prim_stride == 1:
+        po = o.trace_primary(cam, SEED, prim_sample, mode=O.MODE_REF_TREE)
+        assert np.array_equal(pg["ray"], po["ray"])
+        _assert_hits_match(pg, po, f"{name} full size", _volume_ids(sc))
+    else:
+        pick = np.arange(0, w * h, prim_stride)
+        rays = pg["ray"][pick]
+        # the same volume draws on both sides: rt_intersect_rays keys ray i as (pixel i, sample 0, bounce 0)
+        ga = g.intersect_rays(rays, 0.001, sc.camera.max_trace_dist, seed=SEED)
+        oa = o.intersect_rays(rays, 0.001, sc.camera.max_trace_dist, seed=SEED, mode=O.MODE_REF_TREE)
+        _assert_hits_match(ga, oa, f"{name} full size (oracle on the GPU's camera rays)", _volume_ids(sc))
+        vol = np.isin(pg["obj"][pick], _volume_ids(sc)) | np.isin(ga["obj"], _volume_ids(sc))
+        assert np.array_equal(pg["obj"][pick][~vol], ga["obj"][~vol]) and np.array_equal(pg["prim"][pick][~vol], ga["prim"][~vol])
+    return sc, g, cam, full, st[0]
+
+
+def test_full_size_c2_properties(gpu):
+    """C2 at its full BASELINE size: 1024x1024, 256 spp, depth 10 = 268 M paths."""
+    _full_size_checks("c2", (1024, 1024, 256, 10), (0, 256), [("samples", 3, {}), ("tiles", 4, dict(tile=48))], prim_sample=99)
+
+
+def test_full_size_c3_properties(gpu):
+    """C3 at its full BASELINE size: 1024x1024, 1024 spp, depth 10 = 1.07 G paths; defocus, glass, subsurface volume.
+    Mean radiance agrees with a 64x64 oracle render of the same scene to Monte-Carlo accuracy."""
+    from cs397raytracingsp22_b200 import scenes
+    sc, g, cam, full, st = _full_size_checks("c3", (1024, 1024, 1024, 10), (0, 1024), [("samples", 2, {})], prim_sample=500)
+    lin, _ = D.resolve(g, cam, full, cam.aa_sample_count)
+    small = scenes.make_scene("c3", width=64, height=64, spp=256)
+    lin_o, _, _ = O.lower_to_oracle(small).render(small.camera.to_c(), seed=3)
+    assert abs(float(lin.mean()) - float(lin_o.mean())) < 0.02 * float(lin_o.mean())
+
+
+def test_full_resolution_c5_properties(gpu):
+    """C5 at its full resolution and depth (3840x2160, 256 instances, 2048^2 maps, depth 10) with a window of 8 of the
+    4096 sample indices: 66 M paths.  Primary hits of one sample index on every 7th pixel (1.2 M rays, across all
+    instances) against the reference-tree oracle - this is the scene where the guard boxes matter."""
+    sc, g, cam, full, st = _full_size_checks("c5", (3840, 2160, 4096, 10), (2040, 2048),
+                                             [("samples", 4, {}), ("tiles", 8, dict(tile=64))], prim_sample=4000, prim_stride=7)
+    assert g.lower_info()["guard_boxes"] > 0 and len(sc.objects) >= 256
+
+
+def test_independent_keys_per_rank_add_up(gpu, small_scenes):
+    """`bench.py --shard weak` (kept as an option): rank r renders the whole frame with key seed + r and the integer
+    accumulators are summed, i.e. an image of N x spp samples whose stratification repeats N times.  Its accumulator is
+    the sum of the single renders, and each of those tracks the oracle run with the same key."""
+    import torch
+    sc = small_scenes("c4")
+    g, o = _both(sc)
+    cam = sc.camera.to_c()
+    dev = torch.device("cuda", 0)
+    both = D.new_accum(cam.screen_width, cam.screen_height, dev)
+    singles = []
+    for r in range(2):
+        D.render_shard(g, cam, D.shard_opts(0, 1, SEED + r, "all"), both)
+        acc = D.new_accum(cam.screen_width, cam.screen_height, dev)
+        D.render_shard(g, cam, D.shard_opts(0, 1, SEED + r, "all"), acc)
+        singles.append(acc)
+    torch.cuda.synchronize()
+    assert torch.equal(both, singles[0] + singles[1])
+    lin, _ = D.resolve(g, cam, both, 2 * cam.aa_sample_count)
+    lin_o = sum(o.render(cam, seed=SEED + r, mode=O.MODE_REF_TREE)[0] for r in range(2)) / 2.0
+    diff = np.abs(lin.cpu().numpy() - lin_o)
+    assert np.median(diff) <= 1e-5 and (diff.max(axis=2) > 1e-3 * np.maximum(lin_o.max(axis=2), float(lin_o.mean()))).mean() < 0.03
 
 
 def test_tiny_instance_far_from_the_origin_of_its_rays(gpu):

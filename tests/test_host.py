@@ -29,7 +29,7 @@ def test_struct_layouts_match_the_header():
     assert C.sizeof(_ffi.rt_material_desc) == 40
     assert C.sizeof(_ffi.rt_camera) == 84
     assert C.sizeof(_ffi.rt_render_opts) == 96
-    assert C.sizeof(_ffi.rt_stats) == 16 * 8 + 4 * 8 + 2 * 8
+    assert C.sizeof(_ffi.rt_stats) == 16 * 8 + 4 * 8 + 3 * 8
 
 
 def test_no_gpu_is_a_loud_error_not_a_fallback(rtlib):
