@@ -593,12 +593,13 @@ void set_affine_row(float* m) {
   m[15] = 1.0f;
 }
 
-// RT_ENGINE_AUTO.  Measured on B200: scenes without large instanced meshes (C1-C3) spend most of a
-// wavefront iteration moving path state through HBM, and the megakernel removes that; where traversal dominates and
-// the sorted wavefront keeps warps coherent (C4, C5) the wavefront engine stays ahead.
-uint32_t pick_engine(bool phong, bool counters, unsigned long long inst_tris) {
+// RT_ENGINE_AUTO.  Measured on B200 (profiles/r2_notes.md): the megakernel wins where there is next to
+// nothing to traverse and a wavefront iteration is mostly path state moving through HBM (C1: +22..51 %); as soon as
+// rays diverge in the BVH or in the material code, warps of sorted wavefront batches beat warps of unrelated paths
+// (C2 -17 %, C3 -9..26 %, C4 -47 %, C5 -38 %).
+uint32_t pick_engine(bool phong, bool counters, unsigned long long inst_tris, size_t bounded_objects) {
   if (phong || counters) return RT_ENGINE_WAVEFRONT;
-  return inst_tris < 16384ull ? RT_ENGINE_MEGAKERNEL : RT_ENGINE_WAVEFRONT;
+  return (inst_tris == 0 && bounded_objects <= 4) ? RT_ENGINE_MEGAKERNEL : RT_ENGINE_WAVEFRONT;
 }
 
 }  // namespace
@@ -812,7 +813,7 @@ int rt_scene_upload(rt_scene* s) try {
   d.mats = s->d_mats.p; d.textures = s->d_textures.p; d.texels = s->d_texels.p; d.planes = s->d_planes.p; d.guards = s->d_guards.p; d.guard_list = s->d_guard_list.p;
   d.tlas_root = L.tlas_root;
   d.tlas_base = L.tlas_base;
-  d.tlas_count = L.tlas_count & ~1u;  // whole child pairs
+  d.tlas_count = L.tlas_count & ~3u;  // whole child groups (pairs, or fours with RT_BVH4)
   d.n_planes = (L.planes.size() == 1 && L.planes[0] < 0) ? 0u : (uint32_t)L.planes.size();
   d.n_objects = (uint32_t)s->objects.size();
   d.n_volumes = L.n_volumes;
@@ -934,7 +935,11 @@ int rt_render_accum(rt_scene* s, const rt_camera* cam, const rt_render_opts* opt
   uint32_t engine = o.engine;
   if (engine == RT_ENGINE_MEGAKERNEL && (fr.phong || counters))
     return fail(RT_ERR_UNSUPPORTED, "ShadingMode::Phong and RT_OPT_COUNTERS run on the wavefront engine only");
-  if (engine == RT_ENGINE_AUTO) engine = pick_engine(fr.phong != 0, counters, inst_tris);
+  if (engine == RT_ENGINE_AUTO) {
+    size_t bounded = 0;
+    for (const auto& ob : s->objects) bounded += ob.kind != RT_OBJ_PLANE ? 1u : 0u;
+    engine = pick_engine(fr.phong != 0, counters, inst_tris, bounded);
+  }
   if (engine == RT_ENGINE_MEGAKERNEL) return run_megakernel(s, fr, total, (long long*)d_accum, st, o.blocks_per_sm, stats);
   return run_wavefront(s, fr, total, (long long*)d_accum, counters, (o.flags & RT_OPT_NO_EVENTS) == 0, st, o.blocks_per_sm,
                        stats);

@@ -26,15 +26,22 @@
 #ifndef RT_OCTANT_SORT
 #define RT_OCTANT_SORT 1
 #endif
-// TLAS nodes (32 B each, breadth-first from the root) every persistent block keeps in shared memory; 0 = none.
-// Must be even (child pairs).
-#ifndef RT_TLAS_SMEM
-#define RT_TLAS_SMEM 128
+// Children per interior node: 2 (64-byte pairs) or 4 with -DRT_BVH4=1 (128-byte groups, collapsed from the binary tree
+// by rt_lower.cpp, which must be compiled with the same switch).
+#ifndef RT_BVH4
+#define RT_BVH4 0
 #endif
-// k_trace claims its next chunk of ray indices while it traverses the current one, so the latency of the
-// single-address atomic is hidden behind the traversal
+// TLAS node records (32 B each, breadth-first from the root) every persistent block keeps in shared memory; 0 = none.
+// Must be a multiple of 4.  Measured (profiles/r2_notes.md): 128 records cost 4 % on C4 and C5 (the shared memory
+// comes out of L1, where the BLAS nodes live), 512 records 11 %; so it is off.
+#ifndef RT_TLAS_SMEM
+#define RT_TLAS_SMEM 0
+#endif
+// k_trace can claim its next chunk of ray indices while it traverses the current one (the latency of the
+// single-address atomic hides behind the traversal).  Measured: -0.4 % on C4, -0.7 % on C5 - the 32 resident warps
+// already hide it, and a chunk held back by a slow warp lengthens the tail; so it is off.
 #ifndef RT_CLAIM_PREFETCH
-#define RT_CLAIM_PREFETCH 1
+#define RT_CLAIM_PREFETCH 0
 #endif
 #ifndef RT_EXTEND_MIN_BLOCKS
 #define RT_EXTEND_MIN_BLOCKS 8  // 64 registers per thread -> 32 resident warps per SM

@@ -330,10 +330,72 @@ void build_bvh(std::vector<BPrim>& prims, uint32_t max_leaf, std::vector<BNode>&
   if (!prims.empty()) subdivide(prims, nodes, 0, max_leaf);
 }
 
-// longest root-to-leaf path, in nodes (the traversal stack never holds more entries than this)
+// Children per interior node: 2 (adjacent pairs, 64 B per fetch) or, with -DRT_BVH4=1, 4 (adjacent groups of four
+// 32-byte records, 128 B per fetch; built by collapsing the binary tree).  Measured on the device: DESIGN.md §2.
+#ifndef RT_BVH4
+#define RT_BVH4 0
+#endif
+const uint32_t kWidth = RT_BVH4 ? 4u : 2u;
+const uint32_t kNoChild = 0xFFFFFFFFu;  // link of an unused slot of a 4-wide group (count == 0)
+inline bool empty_slot(const BNode& n) { return n.count == 0 && n.leftFirst == kNoChild; }
+
+// 1 + the most entries the traversal stack can hold below node `ni`: visiting a group pushes all its children but
+// the one it descends into.  For the binary tree this is the longest root-to-leaf path, in nodes.
 uint32_t bvh_depth(const std::vector<BNode>& nodes, uint32_t ni = 0) {
-  if (nodes.empty() || nodes[ni].count) return 1;
-  return 1 + std::max(bvh_depth(nodes, nodes[ni].leftFirst), bvh_depth(nodes, nodes[ni].leftFirst + 1));
+  if (nodes.empty() || nodes[ni].count || empty_slot(nodes[ni])) return 1;
+  uint32_t g = nodes[ni].leftFirst, live = 0, below = 0;
+  for (uint32_t k = 0; k < kWidth; ++k) {
+    if (empty_slot(nodes[g + k])) continue;
+    ++live;
+    below = std::max(below, bvh_depth(nodes, g + k));
+  }
+  return (live ? live - 1 : 0) + below;
+}
+
+// Binary tree (root at 0, child pairs) -> 4-wide tree (root at 0, records 1..3 padding, then one group of four adjacent
+// child records per interior node, breadth first).  A group starts as the two children of its node; while it has a free
+// slot, the interior child with the largest surface area is replaced by its own two children.
+void collapse4(std::vector<BNode>& nodes) {
+  BNode none{};
+  none.leftFirst = kNoChild;
+  none.count = 0;
+  BNode pad{};
+  std::vector<BNode> out;
+  out.reserve(nodes.size() * 2 + 4);
+  out.push_back(nodes.empty() ? pad : nodes[0]);
+  for (int k = 0; k < 3; ++k) out.push_back(pad);
+  if (nodes.size() <= 2 || nodes[0].count) {
+    nodes.swap(out);
+    return;
+  }
+  std::vector<uint32_t> queue{0};  // records of `out` whose link still points into the binary tree
+  for (size_t qi = 0; qi < queue.size(); ++qi) {
+    const uint32_t oi = queue[qi];
+    if (out[oi].count || empty_slot(out[oi])) continue;
+    std::vector<uint32_t> slots{out[oi].leftFirst, out[oi].leftFirst + 1};
+    while (slots.size() < 4) {
+      int best = -1;
+      float best_area = -1.0f;
+      for (size_t k = 0; k < slots.size(); ++k) {
+        const BNode& c = nodes[slots[k]];
+        if (c.count) continue;
+        float a = half_area(c.mn, c.mx);
+        if (a > best_area) {
+          best_area = a;
+          best = (int)k;
+        }
+      }
+      if (best < 0) break;
+      uint32_t l = nodes[slots[best]].leftFirst;
+      slots[best] = l;
+      slots.push_back(l + 1);
+    }
+    const uint32_t g = (uint32_t)out.size();
+    for (uint32_t k = 0; k < 4; ++k) out.push_back(k < slots.size() ? nodes[slots[k]] : none);
+    out[oi].leftFirst = g;
+    for (uint32_t k = 0; k < 4; ++k) queue.push_back(g + k);
+  }
+  nodes.swap(out);
 }
 
 // breadth-first order (root, padding, then child pairs level by level): the first N nodes are the top of the tree,
@@ -447,6 +509,7 @@ void build_mesh(HostMesh& m) {
   std::vector<BNode> nodes;
   g_prim_cost = 1.0f;
   build_bvh(prims, g_leaf_max, nodes);
+  if (RT_BVH4) collapse4(nodes);
   // Conservative traversal: boxes are padded by a few ulps of the largest coordinate so that a
   // triangle the reference's Möller–Trumbore test accepts is never culled by rounding in the
   // slab test (flat boxes of coplanar triangles get thickness this way, cf. Q3).
@@ -568,7 +631,7 @@ int lower_scene(const std::vector<HostTexture>& textures, const std::vector<rt_m
     L.nodes.insert(L.nodes.end(), m.nodes.begin(), m.nodes.end());
     for (size_t q = n0; q < L.nodes.size(); q += 2) {
       uint32_t count = L.nodes[q + 1].u[3];
-      L.nodes[q].u[3] += count ? tri_base[mi] : node_base[mi];
+      if (count || L.nodes[q].u[3] != kNoChild) L.nodes[q].u[3] += count ? tri_base[mi] : node_base[mi];
       for (int k = 0; k < 3; ++k) {
         L.nodes[q].f[k] -= m.pad;
         L.nodes[q + 1].f[k] += m.pad;
@@ -783,7 +846,8 @@ int lower_scene(const std::vector<HostTexture>& textures, const std::vector<rt_m
     g_prim_cost = 1.0f;
     std::vector<BNode> tn;
     build_bvh(tprims, 1, tn);
-    reorder_bfs(tn);
+    if (RT_BVH4) collapse4(tn);  // emits breadth first as well
+    else reorder_bfs(tn);
     L.tlas_depth = bvh_depth(tn);
     for (auto& n : tn)
       if (n.count) n.leftFirst = tprims[n.leftFirst].id;  // leaf -> object index
@@ -791,7 +855,7 @@ int lower_scene(const std::vector<HostTexture>& textures, const std::vector<rt_m
     std::vector<Quad> tq;
     nodes_to_quads(tn, 0.0f, tq);
     for (size_t q = 0; q < tq.size(); q += 2)
-      if (tq[q + 1].u[3] == 0) tq[q].u[3] += base;
+      if (tq[q + 1].u[3] == 0 && tq[q].u[3] != kNoChild) tq[q].u[3] += base;
     L.nodes.insert(L.nodes.end(), tq.begin(), tq.end());
     L.tlas_base = base;
     L.tlas_count = (uint32_t)tn.size();
@@ -812,7 +876,7 @@ int lower_scene(const std::vector<HostTexture>& textures, const std::vector<rt_m
       return RT_ERR_UNSUPPORTED;
     }
   }
-  if (L.nodes.empty()) L.nodes.assign(RT_NODE_QUADS * 2, Quad{});
+  if (L.nodes.empty()) L.nodes.assign(RT_NODE_QUADS * 4, Quad{});
   // final form of the link word: the packed traversal entry (leaf flag | first << 4 | count, or the
   // index of the child pair), so the kernel uses lo.w as is; hi.w keeps the plain count
   for (size_t q = 0; q < L.nodes.size(); q += 2) L.nodes[q].u[3] = pack_entry(L.nodes[q].u[3], L.nodes[q + 1].u[3]);

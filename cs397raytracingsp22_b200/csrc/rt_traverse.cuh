@@ -219,6 +219,59 @@ __device__ __forceinline__ float4 lds_quad(uint32_t addr) {
 }
 #endif
 
+#if RT_BVH4
+// interior node, 4-wide tree: fetch the 128-byte group of four child records (eight 128-bit read-only loads), test
+// the four boxes, continue with the nearest child hit and push the others, farthest first.  Unused slots carry the
+// link RT_ENTRY_NONE.
+__device__ __forceinline__ void cswap(float& ka, uint32_t& la, float& kb, uint32_t& lb) {
+  const bool sw = kb < ka;
+  const float k0 = sw ? kb : ka, k1 = sw ? ka : kb;
+  const uint32_t l0 = sw ? lb : la, l1 = sw ? la : lb;
+  ka = k0; kb = k1; la = l0; lb = l1;
+}
+template <bool COUNT>
+__device__ __forceinline__ void trav_interior(const rt_dev_scene& sc, Trav& T) {
+  const uint32_t e = T.entry;
+  float4 q[8];
+#if RT_TLAS_SMEM
+  const uint32_t rel = e - sc.tlas_base;
+  if (rel < tlas_cached(sc)) {
+    const uint32_t a = T.tbase + rel * 32u;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) q[k] = lds_quad(a + 16u * k);
+  } else
+#endif
+  {
+    const float4* grp = reinterpret_cast<const float4*>(sc.nodes) + (size_t)e * 2u;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) q[k] = __ldg(grp + k);
+  }
+  if (COUNT) {
+    T.cnt.nodes += 4;
+    if (!T.in_blas) T.cnt.tlas_nodes += 4;
+  }
+  float key[4];
+  uint32_t link[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    float tn;
+    link[k] = fbits(q[2 * k].w);
+    bool h = slab(q[2 * k], q[2 * k + 1], T.inv, T.oi, T.t_min, T.best.t, tn) && link[k] != RT_ENTRY_NONE;
+    key[k] = h ? tn : CUDART_INF_F;
+    if (!h) link[k] = RT_ENTRY_NONE;
+  }
+  // sorting network, ascending entry distance; misses (key = +inf, link = NONE) end up last
+  cswap(key[0], link[0], key[1], link[1]);
+  cswap(key[2], link[2], key[3], link[3]);
+  cswap(key[0], link[0], key[2], link[2]);
+  cswap(key[1], link[1], key[3], link[3]);
+  cswap(key[1], link[1], key[2], link[2]);
+  if (link[3] != RT_ENTRY_NONE) T.push(link[3]);
+  if (link[2] != RT_ENTRY_NONE) T.push(link[2]);
+  if (link[1] != RT_ENTRY_NONE) T.push(link[1]);
+  T.entry = link[0];
+}
+#else
 // interior node: fetch the 64-byte child pair with four 128-bit read-only loads, test both boxes,
 // continue with the nearer child and push the other
 template <bool COUNT>
@@ -227,7 +280,7 @@ __device__ __forceinline__ void trav_interior(const rt_dev_scene& sc, Trav& T) {
   float4 l0, l1, r0, r1;
 #if RT_TLAS_SMEM
   const uint32_t rel = e - sc.tlas_base;  // BLAS nodes lie below tlas_base: rel wraps to a huge value
-  if (rel < tlas_cached(sc)) {            // pairs never straddle the end: the cached count is even, like every pair index
+  if (rel < tlas_cached(sc)) {            // groups never straddle the end: the cached count is a multiple of 4
     const uint32_t a = T.tbase + rel * 32u;
     l0 = lds_quad(a); l1 = lds_quad(a + 16u); r0 = lds_quad(a + 32u); r1 = lds_quad(a + 48u);
   } else
@@ -253,6 +306,7 @@ __device__ __forceinline__ void trav_interior(const rt_dev_scene& sc, Trav& T) {
     T.entry = hl ? el : (hr ? er : RT_ENTRY_NONE);
   }
 }
+#endif
 
 // leaf: BLAS leaf = up to RT_MAX_LEAF_TRIS triangle records; TLAS leaf = one top-level object
 template <bool COUNT, bool VOLMESH>
