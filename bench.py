@@ -49,7 +49,9 @@ def parse_args():
     ap.add_argument("--tile", type=int, default=TILE)
     ap.add_argument("--engine", default="auto", choices=["auto", "wavefront", "megakernel"])
     ap.add_argument("--ray-sort", default="auto", choices=["auto", "off", "on"])
+    ap.add_argument("--work-order", default="auto", choices=["auto", "pixel", "sample", "grouped"])
     ap.add_argument("--blocks-per-sm", type=int, default=0)
+    ap.add_argument("--no-counters", action="store_true", help="skip the counted pass (profiling runs; zeroes the roofline)")
     ap.add_argument("--wavefront", type=int, default=0)
     ap.add_argument("--spp", type=int, default=0, help="override samples per pixel (invalidates the headline)")
     ap.add_argument("--width", type=int, default=0)
@@ -184,7 +186,7 @@ def cpu_render_sample(sc, n_spp: int, first: int = 0):
 
 def cpu_baseline(sc, target_seconds: float) -> dict:
     s, r, dt, cores = cpu_render_sample(sc, 1)
-    n = max(1, min(int(target_seconds / max(dt, 1e-3)) - 1, sc.camera.aa_sample_count - 1, 16))
+    n = max(1, min(int(target_seconds / max(dt, 1e-3)) - 1, sc.camera.aa_sample_count - 1, 64))
     if n >= 1 and dt < target_seconds * 0.6:
         s2, r2, dt2, _ = cpu_render_sample(sc, n, first=1)
         s, r, dt = s + s2, r + r2, dt + dt2
@@ -263,6 +265,7 @@ class Job:
         a, D, F = self.args, self.D, self.ffi
         kw = dict(wavefront=a.wavefront, flags=flags, engine=F.ENGINES[engine or a.engine],
                   ray_sort={"auto": 0, "off": 1, "on": 2}[a.ray_sort], blocks_per_sm=a.blocks_per_sm, tile=a.tile,
+                  work_order={"auto": 0, "pixel": 1, "sample": 2, "grouped": 3}[a.work_order],
                   sample_end=sample_end)
         if a.emulate_shards:
             return D.shard_opts(0, a.emulate_shards, SEED, self.shard, **kw)
@@ -379,9 +382,12 @@ def main():
 
     # counted pass (untimed, wavefront engine: the device counters live there): same keys => same rays => same counts
     counted = {}
-    job.step(job.opts(flags=_ffi.RT_OPT_COUNTERS, engine="wavefront"), counted)
+    if args.no_counters:
+        counted = {k: 0 for k in _ffi.rt_stats().as_dict()}
+    else:
+        job.step(job.opts(flags=_ffi.RT_OPT_COUNTERS, engine="wavefront"), counted)
     torch.cuda.synchronize()
-    for _ in range(max(args.warmup, 3)):
+    for _ in range(args.warmup):
         job.step(job.opts())
     torch.cuda.synchronize()
 
@@ -514,7 +520,7 @@ def main():
         cpu = cpu_baseline(job.sc, args.cpu_seconds)
 
     line = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms / args.steps, "higher_is_better": True,
         "scaling": scaling_of(args),
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",

@@ -111,6 +111,8 @@ SIGNATURES = {
     "rt_render_accum": (C.c_int, [_P, C.POINTER(rt_camera), C.POINTER(rt_render_opts), _P, _P, C.POINTER(rt_stats)]),
     "rt_resolve": (C.c_int, [_P, C.POINTER(rt_camera), _P, C.c_uint32, _P, _P, _P]),
     "rt_accum_bytes": (C.c_size_t, [C.c_uint32, C.c_uint32]),
+    "rt_render_progressive": (C.c_int, [_P, C.POINTER(rt_camera), C.POINTER(rt_render_opts), C.POINTER(C.c_int64), C.c_uint32,
+                                        _F, _U8, C.POINTER(rt_stats)]),
     "rt_trace_primary": (C.c_int, [_P, C.POINTER(rt_camera), C.c_uint64, C.c_uint32, _I, _I, _F, _F, _F]),
     "rt_intersect_rays": (C.c_int, [_P, C.c_uint64, C.c_uint32, _F, C.c_float, C.c_float, _I, _I, _F, _F, _F, _F, _I]),
     "rt_obj_parse": (C.c_int, [C.c_char_p, C.c_size_t, C.POINTER(rt_obj_mesh)]),
@@ -351,6 +353,20 @@ class GpuBackend:
         o = opts if opts is not None else rt_render_opts()
         check(self.lib.rt_render(self.handle, C.byref(cam), C.byref(o), fptr(lin.reshape(-1)) if lin is not None else None,
                                  u8ptr(rgb.reshape(-1)) if rgb is not None else None, C.byref(st)))
+        return lin, rgb, st
+
+    def render_progressive(self, cam: rt_camera, opts: rt_render_opts, accum: np.ndarray, spp_in_accum: int,
+                           want_linear=True, want_rgb8=True):
+        """Adds opts.sample_begin..sample_end to the HOST accumulator `accum` (int64, H*W*4; the checkpoint) and
+        resolves the image of the spp_in_accum samples per pixel it then holds."""
+        w, h = cam.screen_width, cam.screen_height
+        assert accum.dtype == np.int64 and accum.size == h * w * 4 and accum.flags["C_CONTIGUOUS"]
+        lin = np.empty((h, w, 3), np.float32) if want_linear else None
+        rgb = np.empty((h, w, 3), np.uint8) if want_rgb8 else None
+        st = rt_stats()
+        check(self.lib.rt_render_progressive(self.handle, C.byref(cam), C.byref(opts), accum.ctypes.data_as(C.POINTER(C.c_int64)),
+                                             spp_in_accum, fptr(lin.reshape(-1)) if lin is not None else None,
+                                             u8ptr(rgb.reshape(-1)) if rgb is not None else None, C.byref(st)))
         return lin, rgb, st
 
     def render_accum(self, cam: rt_camera, opts: rt_render_opts, d_accum_ptr: int, stream_ptr: int = 0) -> rt_stats:

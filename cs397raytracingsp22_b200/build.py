@@ -36,6 +36,8 @@ def _host_cxx() -> list[str]:
 def needs_build() -> bool:
     if not os.path.exists(LIB):
         return True
+    if os.environ.get("RT_B200_LIB"):
+        return False  # an explicitly named A/B build is used as it is (it was built with its own -D switches)
     t = os.path.getmtime(LIB)
     deps = [os.path.join(CSRC, f) for f in SOURCES + HEADERS] + [os.path.abspath(__file__)]
     return any(os.path.getmtime(d) > t for d in deps)

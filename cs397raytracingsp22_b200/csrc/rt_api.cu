@@ -593,13 +593,14 @@ void set_affine_row(float* m) {
   m[15] = 1.0f;
 }
 
-// RT_ENGINE_AUTO.  Measured on B200 (profiles/r2_notes.md): the megakernel wins where there is next to
-// nothing to traverse and a wavefront iteration is mostly path state moving through HBM (C1: +22..51 %); as soon as
-// rays diverge in the BVH or in the material code, warps of sorted wavefront batches beat warps of unrelated paths
-// (C2 -17 %, C3 -9..26 %, C4 -47 %, C5 -38 %).
-uint32_t pick_engine(bool phong, bool counters, unsigned long long inst_tris, size_t bounded_objects) {
+// RT_ENGINE_AUTO.  Measured on B200 (profiles/r2_notes.md C1/C3), megakernel vs wavefront: C1 +64 %,
+// C2 +8 %, C3 -7 %, C4 -47 %, C5 -38 %.  The megakernel wins where there is little to traverse and a wavefront
+// iteration is mostly path state moving through HBM; as soon as the rays of a warp diverge in the BVH (big instanced
+// meshes) or in the material code (many material classes in one scene), warps of sorted wavefront batches beat warps
+// of unrelated paths.
+uint32_t pick_engine(bool phong, bool counters, unsigned long long inst_tris, uint32_t material_classes) {
   if (phong || counters) return RT_ENGINE_WAVEFRONT;
-  return (inst_tris == 0 && bounded_objects <= 4) ? RT_ENGINE_MEGAKERNEL : RT_ENGINE_WAVEFRONT;
+  return (inst_tris < 16384ull && material_classes <= 2) ? RT_ENGINE_MEGAKERNEL : RT_ENGINE_WAVEFRONT;
 }
 
 }  // namespace
@@ -936,9 +937,12 @@ int rt_render_accum(rt_scene* s, const rt_camera* cam, const rt_render_opts* opt
   if (engine == RT_ENGINE_MEGAKERNEL && (fr.phong || counters))
     return fail(RT_ERR_UNSUPPORTED, "ShadingMode::Phong and RT_OPT_COUNTERS run on the wavefront engine only");
   if (engine == RT_ENGINE_AUTO) {
-    size_t bounded = 0;
-    for (const auto& ob : s->objects) bounded += ob.kind != RT_OBJ_PLANE ? 1u : 0u;
-    engine = pick_engine(fr.phong != 0, counters, inst_tris, bounded);
+    uint32_t class_mask = 0;  // material classes that can be hit in this scene
+    for (const auto& ob : s->objects)
+      class_mask |= 1u << (ob.material >= 0 ? s->materials[ob.material].tag : (uint32_t)RT_CLASS_PARAM_TEX);
+    uint32_t classes = 0;
+    for (uint32_t m = class_mask; m; m &= m - 1) ++classes;
+    engine = pick_engine(fr.phong != 0, counters, inst_tris, classes);
   }
   if (engine == RT_ENGINE_MEGAKERNEL) return run_megakernel(s, fr, total, (long long*)d_accum, st, o.blocks_per_sm, stats);
   return run_wavefront(s, fr, total, (long long*)d_accum, counters, (o.flags & RT_OPT_NO_EVENTS) == 0, st, o.blocks_per_sm,
@@ -1007,6 +1011,40 @@ int rt_render(rt_scene* s, const rt_camera* cam, const rt_render_opts* opts, flo
   return RT_OK;
 }
 RT_CATCH("rt_render")
+
+int rt_render_progressive(rt_scene* s, const rt_camera* cam, const rt_render_opts* opts, int64_t* accum,
+                          uint32_t spp_in_accum, float* out_linear, uint8_t* out_rgb8, rt_stats* stats) try {
+  int rc = set_device(s);
+  if (rc != RT_OK) return rc;
+  if ((rc = check_camera(cam)) != RT_OK) return rc;
+  if (!accum) return fail(RT_ERR_INVALID, "rt_render_progressive: accum is NULL");
+  if ((out_linear || out_rgb8) && !spp_in_accum) return fail(RT_ERR_INVALID, "rt_render_progressive: spp_in_accum is 0");
+  const size_t npix = (size_t)cam->screen_width * cam->screen_height, bytes = rt_accum_bytes(cam->screen_width, cam->screen_height);
+  if ((rc = ensure_buf(s->d_accum, bytes)) != RT_OK) return rc;
+  if ((rc = ensure_runtime(s)) != RT_OK) return rc;
+  cudaStream_t st = s->own_stream;
+  CUDA_TRY(cudaMemcpyAsync(s->d_accum.p, accum, bytes, cudaMemcpyHostToDevice, st));   // resume from the checkpoint
+  rt_stats local{};
+  if ((rc = rt_render_accum(s, cam, opts, s->d_accum.p, st, &local)) != RT_OK) return rc;
+  CUDA_TRY(cudaMemcpyAsync(accum, s->d_accum.p, bytes, cudaMemcpyDeviceToHost, st));   // the new checkpoint
+  local.h2d_bytes += bytes;
+  local.d2h_bytes += bytes;
+  if (out_linear && (rc = ensure_buf(s->d_linear, npix * 12)) != RT_OK) return rc;
+  if (out_rgb8 && (rc = ensure_buf(s->d_rgb8, npix * 3)) != RT_OK) return rc;
+  if (out_linear || out_rgb8) {
+    rt::launch_resolve((const long long*)s->d_accum.p, (uint32_t)npix, spp_in_accum, cam->gamma,
+                       out_linear ? (float*)s->d_linear.p : nullptr, out_rgb8 ? (uint8_t*)s->d_rgb8.p : nullptr, st);
+    local.kernel_launches += 1;
+    if (out_linear) CUDA_TRY(cudaMemcpyAsync(out_linear, s->d_linear.p, npix * 12, cudaMemcpyDeviceToHost, st));
+    if (out_rgb8) CUDA_TRY(cudaMemcpyAsync(out_rgb8, s->d_rgb8.p, npix * 3, cudaMemcpyDeviceToHost, st));
+    local.d2h_bytes += (out_linear ? npix * 12 : 0) + (out_rgb8 ? npix * 3 : 0);
+  }
+  CUDA_TRY(cudaStreamSynchronize(st));
+  CUDA_TRY(cudaGetLastError());
+  if (stats) *stats = local;
+  return RT_OK;
+}
+RT_CATCH("rt_render_progressive")
 
 // ---- parity hooks: one k_extend launch in debug mode, results copied back
 static int trace_common(rt_scene* s, const rt_frame& fr, unsigned long long total, uint32_t n, const float* ray_od,

@@ -270,6 +270,9 @@ __global__ void __launch_bounds__(RT_BLOCK) k_surface(rt_dev_scene sc, rt_ctrl* 
 #ifndef RT_SHADE_MIN_BLOCKS
 #define RT_SHADE_MIN_BLOCKS 10
 #endif
+#ifndef RT_SHADE_WARP_SCAN
+#define RT_SHADE_WARP_SCAN 1
+#endif
 // MULTI (Camera::path_samples > 1): the kernel runs once per child index fr.branch over the same hits; a child's
 // random numbers are keyed by its position in the sample's path tree (carried in C.w), its throughput is divided by
 // path_samples (tracing.rs:319), and the hit's emission is added by the first pass only.
@@ -347,6 +350,20 @@ __global__ void __launch_bounds__(RT_BLOCK, RT_SHADE_MIN_BLOCKS) k_shade(rt_dev_
     if (oct == k) my_bal = bk;
   }
   __syncthreads();
+#if RT_WARPS == 4 && RT_SHADE_WARP_SCAN
+  if (warp == 0) {  // the 8 x 4 counters are exactly one warp's worth: exclusive prefix by shuffles, octant-major
+    uint32_t* cnt = &s_ocount[0][0];
+    const uint32_t c = cnt[lane];
+    uint32_t inc = c;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+      uint32_t t = __shfl_up_sync(0xFFFFFFFFu, inc, off);
+      if (lane >= (uint32_t)off) inc += t;
+    }
+    cnt[lane] = inc - c;
+    if (lane == 31) s_base = inc ? atomicAdd(&ctrl->n_next, inc) : 0u;
+  }
+#else
   if (threadIdx.x == 0) {
     uint32_t total = 0;
 #pragma unroll
@@ -359,6 +376,7 @@ __global__ void __launch_bounds__(RT_BLOCK, RT_SHADE_MIN_BLOCKS) k_shade(rt_dev_
       }
     s_base = total ? atomicAdd(&ctrl->n_next, total) : 0u;
   }
+#endif
   __syncthreads();
   if (alive) {
     uint32_t pos = s_base + s_ocount[oct][warp] + __popc(my_bal & ((1u << lane) - 1u));
@@ -406,11 +424,15 @@ __global__ void __launch_bounds__(RT_BLOCK, RT_SHADE_MIN_BLOCKS) k_shade(rt_dev_
 // traverses, in the layout of the wavefront's ray queue (A, B, C quads), so the traversal code re-reads the world
 // ray and the RNG coordinates through the same pointers it uses there.  Images are bit-identical to the wavefront
 // engine's: same functions, same Philox keys, integer accumulation.
+// Measured (profiles/r2_notes.md C1, C3): 8 resident blocks (64 registers) beat 6 (80 registers) by 15-18 % on the scenes
+// this engine is for - occupancy hides the shared-memory and L1 latency of the phase changes; and refilling only when
+// at least 8 lanes are idle is within noise of refilling at once on C4 and happens to steer ptxas away from ~100 B of
+// spills in the traversal loop, which alone is worth 20 % (same source, RT_PATH_REGEN_MIN 1 vs 8).
 #ifndef RT_PATH_MIN_BLOCKS
-#define RT_PATH_MIN_BLOCKS 6
+#define RT_PATH_MIN_BLOCKS 8
 #endif
 #ifndef RT_PATH_REGEN_MIN
-#define RT_PATH_REGEN_MIN 1   // idle lanes that trigger a regeneration round (an all-idle warp always regenerates)
+#define RT_PATH_REGEN_MIN 8   // idle lanes that trigger a regeneration round (an all-idle warp always regenerates)
 #endif
 #ifndef RT_PATH_CHUNK_MAX
 #define RT_PATH_CHUNK_MAX 256  // work indices a warp claims per global atomic (guided: shrinks towards the end of the shard)
@@ -439,13 +461,15 @@ __global__ void __launch_bounds__(RT_BLOCK, RT_PATH_MIN_BLOCKS) k_path(rt_dev_sc
   T.k0 = fr.k0; T.k1 = fr.k1;
   T.qA = sA; T.qB = sB; T.qC = sC;
   T.slot = tid;
-  const unsigned long long total = ctrl->total;
-  const unsigned long long claimers = 4ull * gridDim.x * RT_WARPS;
   bool have = false;
-  unsigned long long c_base = 0;       // this warp's claimed chunk of work indices (warp uniform)
-  uint32_t c_off = 0, c_cnt = 0;
+  // this warp's claimed chunk of work indices lives in shared memory (warp-uniform values; registers are what limits
+  // the occupancy of this kernel): s_chunk[warp] = {base lo, base hi, next offset, count}
+  __shared__ uint32_t s_chunk[RT_WARPS][4];
+  uint32_t* const chunk = s_chunk[tid >> 5];
+  if (lane < 4) chunk[lane] = 0u;
+  __syncwarp();
   bool exhausted = false;              // the shard has no more chunks (warp uniform)
-  uint32_t n_rays = 0, n_started = 0, n_invalid = 0;
+  uint32_t n_rays = 0;
 
   for (;;) {
     // ---- regeneration: idle lanes start the next camera paths of this warp's chunk
@@ -453,14 +477,16 @@ __global__ void __launch_bounds__(RT_BLOCK, RT_PATH_MIN_BLOCKS) k_path(rt_dev_sc
     if (need == FULL || __popc(need) >= RT_PATH_REGEN_MIN) {
 #pragma unroll 1
       for (int round = 0; round < 2 && need; ++round) {
+        uint32_t c_off = chunk[2], c_cnt = chunk[3];
         if (c_off >= c_cnt) {
           if (exhausted) break;
+          const unsigned long long total = ctrl->total;
           unsigned long long base = 0;
           uint32_t cnt = 0;
           if (lane == 0) {
             // guided self-scheduling: large chunks while there is plenty of work, 32 at the end (load balance of the tail)
             unsigned long long cur = *reinterpret_cast<volatile unsigned long long*>(&ctrl->cursor);
-            unsigned long long want = cur < total ? (total - cur) / claimers : 0ull;
+            unsigned long long want = cur < total ? (total - cur) / (4ull * gridDim.x * RT_WARPS) : 0ull;
             cnt = want >= RT_PATH_CHUNK_MAX ? (uint32_t)RT_PATH_CHUNK_MAX : (want < 32ull ? 32u : ((uint32_t)want & ~31u));
             base = atomicAdd(&ctrl->cursor, (unsigned long long)cnt);
           }
@@ -471,13 +497,20 @@ __global__ void __launch_bounds__(RT_BLOCK, RT_PATH_MIN_BLOCKS) k_path(rt_dev_sc
             break;
           }
           unsigned long long left = total - base;
-          c_base = base;
           c_off = 0;
           c_cnt = left < (unsigned long long)cnt ? (uint32_t)left : cnt;
+          __syncwarp();
+          if (lane == 0) {
+            chunk[0] = (uint32_t)base;
+            chunk[1] = (uint32_t)(base >> 32);
+            chunk[3] = c_cnt;
+          }
+          __syncwarp();
         }
         const uint32_t avail = c_cnt - c_off;
         const uint32_t rank = __popc(need & ((1u << lane) - 1u));
         if (!have && rank < avail) {
+          const unsigned long long c_base = (unsigned long long)chunk[0] | ((unsigned long long)chunk[1] << 32);
           uint32_t x, y, sample;
           if (work_to_pixel(fr, c_base + c_off + rank, x, y, sample)) {
             uint32_t pixel = y * fr.width + x;
@@ -487,17 +520,18 @@ __global__ void __launch_bounds__(RT_BLOCK, RT_PATH_MIN_BLOCKS) k_path(rt_dev_sc
             sB[tid] = make_float4(d.y, d.z, 1.0f, 1.0f);
             sC[tid] = make_float4(1.0f, __uint_as_float(pixel), __uint_as_float(sample), 0.0f);  // bounce 0
             have = true;
-            ++n_started;
           } else {
-            ++n_invalid;  // tile slot outside the image: the index is spent, the lane asks again
+            atomicAdd(&ctrl->counters[7], 1ull);  // tile slot outside the image: the index is spent, the lane asks again
           }
         }
-        c_off += min((uint32_t)__popc(need), avail);
+        __syncwarp();
+        if (lane == 0) chunk[2] = c_off + min((uint32_t)__popc(need), avail);
+        __syncwarp();
         need = __ballot_sync(FULL, !have);
       }
     }
     if (!__any_sync(FULL, have)) {
-      if (exhausted && c_off >= c_cnt) break;
+      if (exhausted && chunk[2] >= chunk[3]) break;
       continue;
     }
 
@@ -535,15 +569,11 @@ __global__ void __launch_bounds__(RT_BLOCK, RT_PATH_MIN_BLOCKS) k_path(rt_dev_sc
       }
     }
   }
-  // ---- bookkeeping: one atomic per warp and counter
+  // ---- bookkeeping: one atomic per warp.  Every claimed index was started or counted as an invalid tile slot, so the
+  // number of camera paths is the number of claimed indices.
   n_rays = __reduce_add_sync(FULL, n_rays);
-  n_started = __reduce_add_sync(FULL, n_started);
-  n_invalid = __reduce_add_sync(FULL, n_invalid);
-  if (lane == 0) {
-    atomicAdd(&ctrl->n_rays_total, (unsigned long long)n_rays);
-    atomicAdd(&ctrl->n_samples, (unsigned long long)(n_started + n_invalid));
-    if (n_invalid) atomicAdd(&ctrl->counters[7], (unsigned long long)n_invalid);
-  }
+  if (lane == 0) atomicAdd(&ctrl->n_rays_total, (unsigned long long)n_rays);
+  if (blockIdx.x == 0 && tid == 0) ctrl->n_samples = ctrl->total;
 }
 
 // ------------------------------------------------------------------ k_raysort_scan / k_raysort_scatter

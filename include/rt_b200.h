@@ -236,6 +236,16 @@ int rt_resolve(rt_scene* s, const rt_camera* cam, const void* d_accum, uint32_t 
                float* d_out_linear_rgb, uint8_t* d_out_rgb8, void* stream);
 size_t rt_accum_bytes(uint32_t width, uint32_t height);
 
+/* Progressive / checkpointed rendering, host buffers.  Adds the sample indices
+ * [opts->sample_begin, opts->sample_end) of every pixel to the HOST accumulator `accum` (W*H*4 int64, rt_accum_bytes();
+ * zero it before the first call) and, if an output pointer is given, resolves the image of the `spp_in_accum` samples
+ * per pixel the accumulator holds after this call.  The accumulator IS the checkpoint: write it to disk, read it back
+ * in another process, continue with the next sample range.  Because the sums are integers and the RNG is keyed on
+ * (pixel, sample, bounce), a render that was interrupted and resumed any number of times is bit-identical to one that
+ * was not.  The reference has no counterpart: its render_to_image (tracing.rs:221-263) is all or nothing. */
+int rt_render_progressive(rt_scene* s, const rt_camera* cam, const rt_render_opts* opts, int64_t* accum,
+                          uint32_t spp_in_accum, float* out_linear_rgb, uint8_t* out_rgb8, rt_stats* stats);
+
 /* Parity hooks (no counterpart in the reference; they expose what
  * Scene::intersect_ray, tracing.rs:327-346, returns).
  * rt_trace_primary: for every pixel, the camera ray of sample index `sample`

@@ -112,3 +112,30 @@ def test_auto_engine_and_refusals(gpu, small_scenes):
     o.reserved[2] = 1
     with pytest.raises(_ffi.RtError):
         g.render(cam, o)
+
+
+def test_checkpointed_render_resumes_bit_for_bit(gpu, small_scenes, tmp_path):
+    """rt_render_progressive: the host accumulator is the checkpoint.  Render sample indices [0, 5),
+    write the accumulator to disk, throw the scene handle away, load the file in a fresh handle, continue with [5, 16):
+    the result is the image - and the accumulator - of an uninterrupted 16-spp render, bit for bit."""
+    sc = small_scenes("c4")
+    cam = sc.camera.to_c()
+    spp = cam.aa_sample_count
+    g = sc.commit(0)
+    o = _ffi.rt_render_opts(); o.seed = SEED
+    lin_ref, rgb_ref, _ = g.render(cam, o)
+    acc = np.zeros(cam.screen_height * cam.screen_width * 4, np.int64)
+    o.sample_begin, o.sample_end = 0, 5
+    lin5, _, st = g.render_progressive(cam, o, acc, 5)
+    assert st.samples == cam.screen_width * cam.screen_height * 5 and np.isfinite(lin5).all()
+    np.save(tmp_path / "ckpt.npy", acc)
+    g.close()
+    sc2 = small_scenes("c4", width=cam.screen_width)      # a second, independently lowered scene object
+    g2 = sc2.commit(0)
+    acc2 = np.load(tmp_path / "ckpt.npy")
+    o.sample_begin, o.sample_end = 5, spp
+    lin, rgb, _ = g2.render_progressive(cam, o, acc2, spp)
+    assert np.array_equal(lin, lin_ref) and np.array_equal(rgb, rgb_ref)
+    # and the accumulator equals the one-shot accumulator
+    one, _ = _accum(g2, cam, [D.shard_opts(0, 1, SEED, "all")])
+    assert np.array_equal(one.cpu().numpy(), acc2)

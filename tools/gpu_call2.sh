@@ -16,6 +16,6 @@ echo "== reference arm"
 timeout 600 python bench.py --impl reference --gpus 1 --steps 3 --warmup 1 > gpurun_out/bench_r2a_ref.json 2> gpurun_out/bench_r2a_ref.err; echo "ref rc=$?"; cut -c1-600 gpurun_out/bench_r2a_ref.json
 echo "== steady-state ncu capture (k_trace / k_shade launches from the middle of a frame)"
 BENCH="python bench.py --steps 1 --warmup 3 --spp 256 --no-cpu-baseline --no-e2e --no-configs"
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:"k_trace|k_shade" -s 150 -c 4 -o gpurun_out/prof_r2a -f $BENCH > gpurun_out/ncu_r2a.log 2>&1; echo "ncu rc=$?"
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:"k_trace|k_shade" -s 130 -c 4 -o gpurun_out/prof_r2a -f $BENCH > gpurun_out/ncu_r2a.log 2>&1; echo "ncu rc=$?"
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -s 400 -c 300 --csv --log-file gpurun_out/launches_r2a.csv $BENCH > gpurun_out/ncu_r2a_list.log 2>&1; echo "ncu list rc=$?"
 ls -la gpurun_out/prof_r2a* gpurun_out/launches_r2a.csv
