@@ -13,6 +13,7 @@
 #include <new>
 #include <stdexcept>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "rt_kernels.h"
@@ -45,6 +46,8 @@ struct rt_scene {
 
   // lowered (host) + resident (device)
   rt::Lowered low;
+  std::vector<void*> pinned;  // lowered arrays registered as page-locked memory, so rt_scene_upload copies at bus speed
+  bool pin_tried = false;
   bool lowered = false;
   bool committed = false;
   int device = -1;
@@ -102,6 +105,27 @@ int ensure_buf(DevBuf& b, size_t bytes) {
   b.bytes = std::max<size_t>(bytes, 16);
   return RT_OK;
 }
+// The big lowered arrays (texels, nodes, triangle and shading records) are page-locked in place on the first upload:
+// a copy from pageable memory is staged through the driver's bounce buffers at a fraction of the bus speed.
+void unpin_lowered(rt_scene* s) {
+  for (void* p : s->pinned) cudaHostUnregister(p);
+  s->pinned.clear();
+  s->pin_tried = false;
+}
+void pin_lowered(rt_scene* s) {
+  if (s->pin_tried) return;
+  s->pin_tried = true;
+  const rt::Lowered& L = s->low;
+  const std::pair<const void*, size_t> arrays[] = {
+      {L.texels.data(), L.texels.size() * 4}, {L.nodes.data(), L.nodes.size() * 16}, {L.tris.data(), L.tris.size() * 16},
+      {L.shade.data(), L.shade.size() * 16}};
+  for (const auto& a : arrays) {
+    if (a.second < (1u << 16)) continue;
+    if (cudaHostRegister(const_cast<void*>(a.first), a.second, cudaHostRegisterDefault) == cudaSuccess) s->pinned.push_back(const_cast<void*>(a.first));
+    else cudaGetLastError();  // not fatal: that array is copied from pageable memory
+  }
+}
+
 int upload(DevBuf& b, const void* src, size_t bytes, cudaStream_t st) {
   int rc = ensure_buf(b, bytes);
   if (rc != RT_OK) return rc;
@@ -289,7 +313,10 @@ int plan_shard(const rt_camera& cam, const rt_render_opts& o, rt_frame& fr, unsi
   // spp otherwise keeps the whole wavefront inside half a tile, which piles the ray-sort keys into a few bins (C5 on
   // 1/8 of the tiles: 1399 -> 1645 Msamples/s).  1: sample-major (a warp = 32 neighbouring pixels), slower everywhere.
   switch (o.work_order) {
-    case RT_ORDER_AUTO: fr.sample_major = o.shard_mode == RT_SHARD_TILES ? 2u : 0u; break;
+    // pixel-major keeps only capacity / spp pixels in flight; at very high spp that is a few thousand pixels, the
+    // ray-sort keys pile into a few bins and the shade queues see one corner of the scene (C5, 4096 spp, full frame:
+    // 1465 pixel-major vs 1688 Msamples/s grouped; C4, 1024 spp: 2586 vs 2567)
+    case RT_ORDER_AUTO: fr.sample_major = (o.shard_mode == RT_SHARD_TILES || se - sb >= 2048u) ? 2u : 0u; break;
     case RT_ORDER_PIXEL_MAJOR: fr.sample_major = 0u; break;
     case RT_ORDER_SAMPLE_MAJOR: fr.sample_major = 1u; break;
     case RT_ORDER_GROUPED: fr.sample_major = 2u; break;
@@ -632,6 +659,7 @@ int rt_scene_create(rt_scene** out) {
 void rt_scene_destroy(rt_scene* s) {
   if (!s) return;
   if (s->device >= 0 && cudaSetDevice(s->device) == cudaSuccess) {
+    unpin_lowered(s);
     free_wavefront(s);
     free_buf(s->d_nodes); free_buf(s->d_tris); free_buf(s->d_shade); free_buf(s->d_objects);
     free_buf(s->d_mats); free_buf(s->d_textures); free_buf(s->d_texels); free_buf(s->d_planes); free_buf(s->d_guards); free_buf(s->d_guard_list);
@@ -798,6 +826,7 @@ int rt_scene_upload(rt_scene* s) try {
   const rt::Lowered& L = s->low;
   int rc;
   cudaStream_t st = 0;
+  pin_lowered(s);
   if ((rc = upload(s->d_nodes, L.nodes.data(), L.nodes.size() * 16, st)) != RT_OK) return rc;
   if ((rc = upload(s->d_tris, L.tris.data(), L.tris.size() * 16, st)) != RT_OK) return rc;
   if ((rc = upload(s->d_shade, L.shade.data(), L.shade.size() * 16, st)) != RT_OK) return rc;
@@ -832,6 +861,8 @@ RT_CATCH("rt_scene_upload")
 int rt_scene_lower(rt_scene* s, rt_lower_info* info) try {
   if (!s) return fail(RT_ERR_INVALID, "scene is NULL");
   std::string err;
+  if (!s->pinned.empty()) unpin_lowered(s);  // the arrays are about to be rebuilt
+  s->pin_tried = false;
   int rc = rt::lower_scene(s->textures, s->materials, s->meshes, s->objects, s->low, err);
   if (rc != RT_OK) return fail(rc, err);
   s->lowered = true;

@@ -118,7 +118,9 @@ def test_checkpointed_render_resumes_bit_for_bit(gpu, small_scenes, tmp_path):
     """rt_render_progressive: the host accumulator is the checkpoint.  Render sample indices [0, 5),
     write the accumulator to disk, throw the scene handle away, load the file in a fresh handle, continue with [5, 16):
     the result is the image - and the accumulator - of an uninterrupted 16-spp render, bit for bit."""
-    sc = small_scenes("c4")
+    from cs397raytracingsp22_b200 import scenes
+    from conftest import SMALL
+    sc = scenes.make_scene("c4", **SMALL["c4"])           # private scene objects: their handles are closed below
     cam = sc.camera.to_c()
     spp = cam.aa_sample_count
     g = sc.commit(0)
@@ -129,8 +131,8 @@ def test_checkpointed_render_resumes_bit_for_bit(gpu, small_scenes, tmp_path):
     lin5, _, st = g.render_progressive(cam, o, acc, 5)
     assert st.samples == cam.screen_width * cam.screen_height * 5 and np.isfinite(lin5).all()
     np.save(tmp_path / "ckpt.npy", acc)
-    g.close()
-    sc2 = small_scenes("c4", width=cam.screen_width)      # a second, independently lowered scene object
+    sc.close()                                            # "the process dies"
+    sc2 = scenes.make_scene("c4", **SMALL["c4"])          # a second, independently lowered scene
     g2 = sc2.commit(0)
     acc2 = np.load(tmp_path / "ckpt.npy")
     o.sample_begin, o.sample_end = 5, spp
@@ -139,3 +141,4 @@ def test_checkpointed_render_resumes_bit_for_bit(gpu, small_scenes, tmp_path):
     # and the accumulator equals the one-shot accumulator
     one, _ = _accum(g2, cam, [D.shard_opts(0, 1, SEED, "all")])
     assert np.array_equal(one.cpu().numpy(), acc2)
+    sc2.close()
