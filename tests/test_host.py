@@ -229,3 +229,61 @@ def test_degenerate_mesh_still_builds_a_bounded_bvh():
                    b.add_material(_ffi.RT_MAT_LAMBERTIAN), [-1] * 5)
     info = b.lower_info()
     assert info["tris"] == n and info["max_blas_depth"] <= 10
+
+
+def test_hostile_png_header_is_refused_before_any_allocation(rtlib):
+    """A 100-byte file whose IHDR promises 65536 x 65536 RGBA16 (a 32 GB image): the reader must return RT_ERR_IO, not
+    reserve the memory, not throw across the ABI."""
+    import struct
+    import zlib
+
+    def chunk(tag, data):
+        return struct.pack(">I", len(data)) + tag + data + struct.pack(">I", zlib.crc32(tag + data) & 0xFFFFFFFF)
+    ihdr = struct.pack(">IIBBBBB", 65536, 65536, 16, 6, 0, 0, 0)
+    bomb = b"\x89PNG\r\n\x1a\n" + chunk(b"IHDR", ihdr) + chunk(b"IDAT", zlib.compress(b"\0" * 64)) + chunk(b"IEND", b"")
+    with pytest.raises(_ffi.RtError) as e:
+        _ffi.png_decode(bomb)
+    assert e.value.code == _ffi.RT_ERR_IO
+    # a stream that inflates to far more than the header's image is cut off, too (zip bomb behind an honest header)
+    ihdr = struct.pack(">IIBBBBB", 4, 4, 8, 2, 0, 0, 0)
+    big = b"\x89PNG\r\n\x1a\n" + chunk(b"IHDR", ihdr) + chunk(b"IDAT", zlib.compress(b"\0" * (64 << 20), 9)) + chunk(b"IEND", b"")
+    with pytest.raises(_ffi.RtError) as e:
+        _ffi.png_decode(big)
+    assert e.value.code == _ffi.RT_ERR_IO
+
+
+def test_caller_supplied_inverse_may_be_off_by_rounding():
+    """cgmath's general Matrix4::invert (geometry.rs:168) leaves w.w = 1 +- an ulp on scaled / rotated transforms; the
+    Rust shim passes that matrix as it is (integration/lower.rs)."""
+    b = _ffi.GpuBackend()
+    mat = b.add_material(_ffi.RT_MAT_LAMBERTIAN)
+    mesh = b.add_mesh(np.eye(3), np.eye(3), np.zeros((3, 2)), np.array([[0, 1, 2]]))
+    x = cg.chain(cg.from_translation((0.0, 1.3, 1.7)), cg.from_angle_y(-60.0), cg.from_scale(0.003))
+    inv = np.linalg.inv(np.asarray(x, np.float64)).astype(np.float32)
+    inv[3, 3] = np.nextafter(np.float32(1.0), np.float32(2.0))          # 1 + ulp
+    inv[3, 0] = 1e-8
+    b.add_instance(mesh, cg.colmajor(x), cg.colmajor(inv), mat, [-1] * 5)   # accepted, row set to (0, 0, 0, 1)
+    inv[3, 3] = 1.001                                                      # a projective matrix is still refused
+    with pytest.raises(_ffi.RtError) as e:
+        b.add_instance(mesh, cg.colmajor(x), cg.colmajor(inv), mat, [-1] * 5)
+    assert e.value.code == _ffi.RT_ERR_UNSUPPORTED
+
+
+def test_objects_that_cannot_be_bounded_are_refused_loudly():
+    b = _ffi.GpuBackend()
+    mat = b.add_material(_ffi.RT_MAT_LAMBERTIAN)
+    b.add_sphere((0.0, float("nan"), 0.0), 1.0, mat)
+    with pytest.raises(_ffi.RtError) as e:
+        b.lower_info()
+    assert e.value.code == _ffi.RT_ERR_UNSUPPORTED and "non-finite" in str(e.value)
+
+
+def test_render_options_are_plain_fields_not_environment_variables():
+    """Round-1 development knobs (RT_LANES, RT_RAY_SORT, RT_SAMPLE_MAJOR, ...) are gone: nothing in the library reads
+    the environment; what remains tunable is a field of rt_render_opts or a -D switch."""
+    for f in ("rt_api.cu", "rt_lower.cpp", "rt_kernels.cu"):
+        assert "getenv" not in open(os.path.join(ROOT, "cs397raytracingsp22_b200", "csrc", f)).read(), f
+    names = [n for n, _ in _ffi.rt_render_opts._fields_]
+    assert names[-5:] == ["engine", "ray_sort", "work_order", "blocks_per_sm", "reserved"]
+    o = D.shard_opts(1, 4, 7, "tiles", tile=16, engine=_ffi.RT_ENGINE_MEGAKERNEL, ray_sort=_ffi.RT_RAYSORT_OFF)
+    assert (o.shard_mode, o.shard_rank, o.shard_count, o.tile_size, o.engine, o.ray_sort) == (2, 1, 4, 16, 2, 1)
