@@ -189,7 +189,7 @@ int ensure_wavefront(rt_scene* s, uint32_t capacity) {
   CUDA_TRY(cudaMalloc((void**)&L.hits.H, n * 16));
   CUDA_TRY(cudaMalloc((void**)&L.hits.obj, n * 4));
   CUDA_TRY(cudaMalloc((void**)&L.queues, n * 4 * RT_NUM_CLASSES));
-  CUDA_TRY(cudaMalloc((void**)&L.sort.keys, n * 4));
+  CUDA_TRY(cudaMalloc((void**)&L.sort.keys, n * 8));  // key (+ rank inside the bin with RT_SORT_RANKED)
   CUDA_TRY(cudaMalloc((void**)&L.sort.order, n * 4));
   if (!L.sort.hist) {
     CUDA_TRY(cudaMalloc((void**)&L.sort.hist, RT_SORT_BINS * 4));

@@ -404,9 +404,18 @@ __global__ void __launch_bounds__(RT_BLOCK, RT_SHADE_MIN_BLOCKS) k_shade(rt_dev_
     if (fr.sort_enabled) {
       // one atomic per distinct key per warp: the rays of a warp mostly leave the same few cells
       uint32_t key = ray_sort_key(fr, no, nd);
-      sort.keys[pos] = key;
       uint32_t peers = __match_any_sync(__activemask(), key);
+#if RT_SORT_RANKED
+      // the histogram atomic hands back the ray's rank inside its bin, so the scatter pass needs no atomics of its own
+      const uint32_t leader = __ffs(peers) - 1u;
+      uint32_t base = 0;
+      if (lane == leader) base = atomicAdd(&sort.hist[key], (uint32_t)__popc(peers));
+      base = __shfl_sync(peers, base, leader);
+      reinterpret_cast<uint2*>(sort.keys)[pos] = make_uint2(key, base + __popc(peers & ((1u << lane) - 1u)));
+#else
+      sort.keys[pos] = key;
       if ((peers & ((1u << lane) - 1u)) == 0) atomicAdd(&sort.hist[key], (uint32_t)__popc(peers));
+#endif
     }
   }
 }
@@ -639,6 +648,11 @@ __global__ void __launch_bounds__(256) k_raysort_scatter(rt_ctrl* __restrict__ c
   __syncthreads();
   if (i >= ctrl->n_next) return;
   // neighbouring queue positions come from the same k_shade block and share keys: one atomic per distinct key per warp
+#if RT_SORT_RANKED
+  const uint2 kr = reinterpret_cast<const uint2*>(sort.keys)[i];
+  sort.order[s_slice[kr.x >> 10] + sort.cursor[kr.x] + kr.y] = i;
+  return;
+#endif
   uint32_t key = sort.keys[i];
   uint32_t peers = __match_any_sync(__activemask(), key);
   uint32_t leader = __ffs(peers) - 1u;
