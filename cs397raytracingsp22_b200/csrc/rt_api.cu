@@ -63,7 +63,7 @@ struct rt_scene {
     rt::rt_sortbuf sort = {};
     rt_ctrl* ctrl = nullptr;     // also the control block of the megakernel engine
     rt_ctrl* h_ctrl = nullptr;   // pinned
-    uint32_t* h_done = nullptr;  // pinned poll slots
+    uint32_t* h_done = nullptr;  // pinned poll slots: 2 x rt_ctrl::poll
     cudaEvent_t poll_ev[2] = {nullptr, nullptr};
     std::vector<cudaEvent_t> events;
   };
@@ -164,7 +164,7 @@ int ensure_runtime(rt_scene* s) {
   rt_scene::Wavefront& L = s->wf;
   CUDA_TRY(cudaMalloc((void**)&L.ctrl, sizeof(rt_ctrl)));
   CUDA_TRY(cudaMallocHost((void**)&L.h_ctrl, sizeof(rt_ctrl)));
-  CUDA_TRY(cudaMallocHost((void**)&L.h_done, 2 * sizeof(uint32_t)));
+  CUDA_TRY(cudaMallocHost((void**)&L.h_done, 2 * 4 * sizeof(uint32_t)));
   CUDA_TRY(cudaEventCreateWithFlags(&L.poll_ev[0], cudaEventDisableTiming));
   CUDA_TRY(cudaEventCreateWithFlags(&L.poll_ev[1], cudaEventDisableTiming));
   return RT_OK;
@@ -374,7 +374,12 @@ int run_wavefront(rt_scene* s, const rt_frame& fr_in, unsigned long long total, 
   if ((rc = ensure_wavefront(s, fr.capacity)) != RT_OK) return rc;
   rt_scene::Wavefront& L = s->wf;
   const uint32_t grid = persistent_grid(s, s->trace_blocks_per_sm, blocks_per_sm);
-  const int kChunk = 8;
+  // Iterations are enqueued two at a time; after each pair the host asks for the control block's poll words and reads the
+  // answer to the request before last, so two to four iterations are always queued ahead of the device and at most
+  // that many empty ones run after the last ray has died (an "empty" iteration is not free: four of its kernels have
+  // grids sized for the whole wavefront).  Once a poll shows the shard exhausted, the ray count it reports bounds
+  // every later iteration (no new paths, survivors only), and the launch grids shrink to it.
+  const int kChunk = 2;
   const size_t kMaxTimedIters = 1u << 14;
   size_t ev_used = 0, timed_iters = 0;
   uint64_t launches = 0, ext = 0, shd = 0;
@@ -394,15 +399,16 @@ int run_wavefront(rt_scene* s, const rt_frame& fr_in, unsigned long long total, 
   CUDA_TRY(cudaEventRecord(ev_begin, st));
   rt::launch_init(L.ctrl, 0ull, total, st);
   launches = 1;
-  L.h_done[0] = L.h_done[1] = 0;
-  bool done = false;
+  std::memset(L.h_done, 0, 2 * 4 * sizeof(uint32_t));
+  bool done = false, exhausted = false;
+  fr.grid_rays = fr.capacity;
   for (int chunk = 0; !done; ++chunk) {
     for (int k = 0; k < kChunk; ++k) {
       int cur = (int)(it & 1), nxt = cur ^ 1;
       rt::launch_advance(L.ctrl, fr.capacity, st);
       bool timed = use_events && timed_iters < kMaxTimedIters;
       cudaEvent_t e0 = nullptr, e1 = nullptr, e2 = nullptr;
-      rt::launch_raygen(fr, L.ctrl, L.paths[cur], st);
+      if (!exhausted) rt::launch_raygen(fr, L.ctrl, L.paths[cur], st);  // an exhausted shard starts no more camera paths
       if (timed) {
         if ((rc = next_event(e0)) != RT_OK || (rc = next_event(e1)) != RT_OK || (rc = next_event(e2)) != RT_OK) return rc;
         CUDA_TRY(cudaEventRecord(e0, st));
@@ -432,16 +438,21 @@ int run_wavefront(rt_scene* s, const rt_frame& fr_in, unsigned long long total, 
         CUDA_TRY(cudaEventRecord(e2, st));
         ++timed_iters;
       }
-      launches += fr.sort_enabled ? 7 : 5; ++ext; ++shd; ++it;
+      launches += (fr.sort_enabled ? 6 : 4) + (exhausted ? 0 : 1); ++ext; ++shd; ++it;
     }
-    // poll: copy the done flag written by k_advance, two chunks deep
+    // poll: the words k_advance wrote, two chunks deep
     int slot = chunk & 1;
+    uint32_t* h = L.h_done + 4 * slot;
     if (chunk >= 2) {
       CUDA_TRY(cudaEventSynchronize(L.poll_ev[slot]));
-      if (L.h_done[slot]) done = true;
+      if (h[0]) done = true;
+      if (h[1] && !fr.phong) {  // (Phong's second k_advance per iteration reports the shadow pass, whose slots do not shrink)
+        exhausted = true;
+        fr.grid_rays = std::min(fr.grid_rays, std::max(h[2], 1u));
+      }
     }
     if (!done) {
-      CUDA_TRY(cudaMemcpyAsync(&L.h_done[slot], &L.ctrl->done, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+      CUDA_TRY(cudaMemcpyAsync(h, L.ctrl->poll, 4 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
       CUDA_TRY(cudaEventRecord(L.poll_ev[slot], st));
     }
   }

@@ -51,6 +51,10 @@ __global__ void k_advance(rt_ctrl* c, uint32_t capacity) {
   else c->iterations += 1;
   c->n_rays_total += n_cont + n_new;
   c->n_samples += n_new;
+  c->poll[0] = c->done;
+  c->poll[1] = c->cursor == c->total ? 1u : 0u;
+  c->poll[2] = n_cont + n_new;
+  c->poll[3] = c->iterations;
 }
 
 // ------------------------------------------------------------------ k_raygen
@@ -813,6 +817,7 @@ __global__ void k_init_ctrl(rt_ctrl* c, unsigned long long begin, unsigned long 
   c->done = 0;
   c->iterations = 0;
   for (int i = 0; i < 12; ++i) c->counters[i] = 0;
+  for (int i = 0; i < 4; ++i) c->poll[i] = 0;
 }
 // Camera::path_samples > 1: the host walks the path tree depth first and tells the device what the next window is
 __global__ void k_set_window(rt_ctrl* c, uint32_t n_cont, uint32_t n_new) {
@@ -855,12 +860,15 @@ void launch_path(const rt_dev_scene& sc, const rt_frame& fr, rt_ctrl* ctrl, long
   if (sc.n_volume_meshes) k_path<true><<<grid, RT_BLOCK, 0, st>>>(sc, fr, ctrl, accum);
   else k_path<false><<<grid, RT_BLOCK, 0, st>>>(sc, fr, ctrl, accum);
 }
+// Launch grids cover fr.grid_rays rays: the wavefront width normally, less once the host knows that the shard is
+// exhausted and only a few rays are left to drain (empty blocks of a 131 072-block grid are not free).
+static inline uint32_t grid_rays(const rt_frame& fr) { return fr.grid_rays ? fr.grid_rays : fr.capacity; }
 void launch_raygen(const rt_frame& fr, rt_ctrl* ctrl, rt_paths cur, cudaStream_t st) {
-  k_raygen<<<(fr.capacity + RT_BLOCK - 1) / RT_BLOCK, RT_BLOCK, 0, st>>>(fr, ctrl, cur);
+  k_raygen<<<(grid_rays(fr) + RT_BLOCK - 1) / RT_BLOCK, RT_BLOCK, 0, st>>>(fr, ctrl, cur);
 }
 void launch_trace(const rt_dev_scene& sc, const rt_frame& fr, rt_ctrl* ctrl, rt_paths cur, rt_hits hits, rt_sortbuf sort,
                   bool count, uint32_t persistent_blocks, cudaStream_t st) {
-  uint32_t full = (fr.capacity + RT_BLOCK - 1) / RT_BLOCK;
+  uint32_t full = (grid_rays(fr) + RT_BLOCK - 1) / RT_BLOCK;
   uint32_t grid = full < persistent_blocks ? full : persistent_blocks;  // never more blocks than there could be rays
   if (sc.n_volume_meshes) {  // the variant that can nest boundary queries (a few more registers)
     if (count) k_trace<true, true><<<grid, RT_BLOCK, 0, st>>>(sc, fr, ctrl, cur, hits, sort.order);
@@ -873,10 +881,10 @@ void launch_trace(const rt_dev_scene& sc, const rt_frame& fr, rt_ctrl* ctrl, rt_
 void launch_raysort(const rt_frame& fr, rt_ctrl* ctrl, rt_sortbuf sort, cudaStream_t st) {
   if (!fr.sort_enabled) return;
   k_raysort_scan<<<RT_SORT_BINS / 1024u, 1024, 0, st>>>(sort);
-  k_raysort_scatter<<<(fr.capacity + 255) / 256, 256, 0, st>>>(ctrl, sort);
+  k_raysort_scatter<<<(grid_rays(fr) + 255) / 256, 256, 0, st>>>(ctrl, sort);
 }
 void launch_sort(const rt_dev_scene& sc, const rt_frame& fr, rt_ctrl* ctrl, rt_hits hits, uint32_t* queues, cudaStream_t st) {
-  k_sort<<<(fr.capacity + RT_SORT_BLOCK - 1) / RT_SORT_BLOCK, RT_SORT_BLOCK, 0, st>>>(sc, fr, ctrl, hits.obj, queues);
+  k_sort<<<(grid_rays(fr) + RT_SORT_BLOCK - 1) / RT_SORT_BLOCK, RT_SORT_BLOCK, 0, st>>>(sc, fr, ctrl, hits.obj, queues);
 }
 void launch_surface(const rt_dev_scene& sc, const rt_frame& fr, rt_ctrl* ctrl, rt_paths cur, rt_hits hits, rt_debug dbg,
                     cudaStream_t st) {
@@ -884,7 +892,7 @@ void launch_surface(const rt_dev_scene& sc, const rt_frame& fr, rt_ctrl* ctrl, r
 }
 void launch_shade(const rt_dev_scene& sc, const rt_frame& fr, rt_ctrl* ctrl, rt_paths cur, rt_paths nxt, rt_hits hits,
                   const uint32_t* queues, long long* accum, rt_sortbuf sort, bool count, cudaStream_t st) {
-  uint32_t grid = (fr.capacity + RT_BLOCK - 1) / RT_BLOCK + RT_NUM_CLASSES;
+  uint32_t grid = (grid_rays(fr) + RT_BLOCK - 1) / RT_BLOCK + RT_NUM_CLASSES;
   if (fr.path_samples > 1) k_shade<false, true><<<grid, RT_BLOCK, 0, st>>>(sc, fr, ctrl, cur, nxt, hits, queues, accum, sort);
   else if (count) k_shade<true, false><<<grid, RT_BLOCK, 0, st>>>(sc, fr, ctrl, cur, nxt, hits, queues, accum, sort);
   else k_shade<false, false><<<grid, RT_BLOCK, 0, st>>>(sc, fr, ctrl, cur, nxt, hits, queues, accum, sort);

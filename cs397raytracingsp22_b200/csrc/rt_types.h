@@ -91,6 +91,7 @@ struct rt_ctrl {
   uint32_t pad_;
   unsigned long long counters[12]; // nodes, tris, instances, prims, mesh_hits, shade taps, mats, invalid tile slots,
                                    // normal-map taps, warp node slots, TLAS nodes, -
+  uint32_t poll[4];                // what the host peeks at: done, exhausted (cursor == total), n_rays, iterations
 };
 
 struct rt_frame {
@@ -106,7 +107,8 @@ struct rt_frame {
   uint32_t sample_begin, sample_count;
   uint32_t sample_major;            // 1: consecutive work indices walk the pixels (sample index changes slowest)
   unsigned long long pixel_slots;   // pixel slots of this shard (work items = pixel_slots * sample_count)
-  uint32_t capacity;                // wavefront width P
+  uint32_t capacity;                // wavefront width P (also the stride of the shade queues)
+  uint32_t grid_rays;               // host-side upper bound of the rays of this iteration: sizes the launch grids (0 => capacity)
   // debug modes of the reference: orthographic projection (tracing.rs:196,200), Phong shading (tracing.rs:277-297)
   uint32_t path_samples, branch;    // Camera::path_samples > 1 (tracing.rs:146,308-319): child index of this k_shade pass
   uint32_t phong;                   // host-side switch: camera ray + shadow ray pairs instead of path iterations
