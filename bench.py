@@ -56,7 +56,8 @@ def parse_args():
     ap.add_argument("--spp", type=int, default=0, help="override samples per pixel (invalidates the headline)")
     ap.add_argument("--width", type=int, default=0)
     ap.add_argument("--height", type=int, default=0)
-    ap.add_argument("--emulate-shards", type=int, default=0, help="diagnostics: render shard 0 of this many (with --shard)")
+    ap.add_argument("--emulate-shards", type=int, default=0, help="diagnostics: render one shard of this many (with --shard)")
+    ap.add_argument("--emulate-rank", type=int, default=0, help="diagnostics: which shard --emulate-shards renders")
     ap.add_argument("--depth", type=int, default=0, help="override path_depth (diagnostics; invalidates the headline)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -268,7 +269,7 @@ class Job:
                   work_order={"auto": 0, "pixel": 1, "sample": 2, "grouped": 3}[a.work_order],
                   sample_end=sample_end)
         if a.emulate_shards:
-            return D.shard_opts(0, a.emulate_shards, SEED, self.shard, **kw)
+            return D.shard_opts(a.emulate_rank, a.emulate_shards, SEED, self.shard, **kw)
         if self.world == 1 or self.shard == "weak":
             return D.shard_opts(0, 1, SEED + (self.rank if self.shard == "weak" else 0), "all", **kw)
         return D.shard_opts(self.rank, self.world, SEED, self.shard, **kw)

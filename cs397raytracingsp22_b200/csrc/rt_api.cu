@@ -75,6 +75,8 @@ struct rt_scene {
   // scratch for host-buffer entry points
   DevBuf d_accum, d_linear, d_rgb8, d_dbg;
   DevBuf d_tree[3];  // ray pool of the depth-first walk (path_samples > 1)
+  DevBuf d_tiles;    // RT_SHARD_TILES: this shard's tile ids
+  std::vector<uint32_t> h_tiles;
 };
 
 namespace {
@@ -267,7 +269,9 @@ void fill_frame_camera(const rt_camera& cam, uint64_t seed, rt_frame& fr) {
 }
 
 // resolves the shard description into (pixel-slot count, sample range); returns work item count
-int plan_shard(const rt_camera& cam, const rt_render_opts& o, rt_frame& fr, unsigned long long& total) {
+// `tiles` (optional) receives the tile ids of a tile shard.
+int plan_shard(const rt_camera& cam, const rt_render_opts& o, rt_frame& fr, unsigned long long& total,
+               std::vector<uint32_t>* tiles = nullptr) {
   uint32_t spp = cam.aa_sample_count;
   uint32_t count = o.shard_count ? o.shard_count : 1;
   if (o.shard_rank >= count) return fail(RT_ERR_INVALID, "shard_rank >= shard_count");
@@ -297,8 +301,21 @@ int plan_shard(const rt_camera& cam, const rt_render_opts& o, rt_frame& fr, unsi
       fr.tile_size = ts;
       fr.tiles_x = (cam.screen_width + ts - 1) / ts;
       fr.tiles_y = (cam.screen_height + ts - 1) / ts;
-      uint32_t ntiles = fr.tiles_x * fr.tiles_y;
-      uint32_t mine = ntiles > o.shard_rank ? (ntiles - o.shard_rank + count - 1) / count : 0;
+      // Which tiles: tile (tx, ty) belongs to rank (tx + stride * ty) mod count - diagonals, not columns.  (Round-robin
+      // over the row-major index degenerates into columns whenever tiles_x is a multiple of count: at 1080p, 16-pixel
+      // tiles and 8 ranks every rank owned the same eight-th of every row, vertical structures of the scene - the
+      // columns of spheres, the drone's flanks - aliased with the 128-pixel period and the slowest rank took 11 % longer
+      // than the fastest.)  stride is the smallest odd number >= 3 that is coprime to count.
+      uint32_t stride = 3;
+      auto gcd = [](uint32_t a, uint32_t b) { while (b) { uint32_t t = a % b; a = b; b = t; } return a; };
+      while (gcd(stride, count) != 1) stride += 2;
+      uint32_t mine = 0;
+      for (uint32_t ty = 0; ty < fr.tiles_y; ++ty)
+        for (uint32_t tx = 0; tx < fr.tiles_x; ++tx)
+          if ((tx + stride * ty) % count == o.shard_rank) {
+            ++mine;
+            if (tiles) tiles->push_back(ty * fr.tiles_x + tx);
+          }
       npix = (unsigned long long)mine * ts * ts;  // slots; those outside the image are skipped
       break;
     }
@@ -676,6 +693,7 @@ void rt_scene_destroy(rt_scene* s) {
     free_buf(s->d_mats); free_buf(s->d_textures); free_buf(s->d_texels); free_buf(s->d_planes); free_buf(s->d_guards); free_buf(s->d_guard_list);
     free_buf(s->d_accum); free_buf(s->d_linear); free_buf(s->d_rgb8); free_buf(s->d_dbg);
     for (auto& b : s->d_tree) free_buf(b);
+    free_buf(s->d_tiles);
     {
       rt_scene::Wavefront& L = s->wf;
       if (L.ctrl) cudaFree(L.ctrl);
@@ -936,7 +954,8 @@ int rt_render_accum(rt_scene* s, const rt_camera* cam, const rt_render_opts* opt
     fr.ambient[k] = o.ambient[k];
   }
   unsigned long long total = 0;
-  if ((rc = plan_shard(*cam, o, fr, total)) != RT_OK) return rc;
+  s->h_tiles.clear();
+  if ((rc = plan_shard(*cam, o, fr, total, &s->h_tiles)) != RT_OK) return rc;
   fr.capacity = pick_capacity(total, o.wavefront);
   if (stats) std::memset(stats, 0, sizeof *stats);
   if (total == 0) return RT_OK;
@@ -946,6 +965,11 @@ int rt_render_accum(rt_scene* s, const rt_camera* cam, const rt_render_opts* opt
   // NULL means the (legacy) default stream, as documented: work must be ordered after whatever the caller has
   // already enqueued there (e.g. the memset of d_accum), which a private non-blocking stream would not be
   cudaStream_t st = (cudaStream_t)stream;
+  if (fr.shard_mode == RT_SHARD_TILES) {  // the shard's tile list; h_tiles lives until the engines have synchronised `st`
+    if ((rc = ensure_buf(s->d_tiles, s->h_tiles.size() * 4)) != RT_OK) return rc;
+    CUDA_TRY(cudaMemcpyAsync(s->d_tiles.p, s->h_tiles.data(), s->h_tiles.size() * 4, cudaMemcpyHostToDevice, st));
+    fr.tile_list = (const uint32_t*)s->d_tiles.p;
+  }
   for (uint32_t r : o.reserved)
     if (r) return fail(RT_ERR_INVALID, "rt_render_opts.reserved must be zero");
   if (o.engine > RT_ENGINE_MEGAKERNEL) return fail(RT_ERR_INVALID, "unknown engine");

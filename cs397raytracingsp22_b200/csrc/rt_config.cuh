@@ -44,9 +44,10 @@
 #define RT_CLAIM_PREFETCH 0
 #endif
 // Ray sort: k_shade keeps the value its histogram atomic returns (= the ray's rank inside its bin), which frees the
-// scatter pass from a second round of atomics at the price of 4 more bytes per ray and an atomic whose result is waited for.
+// scatter pass from a second round of atomics at the price of 4 more bytes per ray and an atomic whose result is waited
+// for.  Measured: +2.1 % on C4, +2.3 % on C5 (profiles/r2_notes.md C6).
 #ifndef RT_SORT_RANKED
-#define RT_SORT_RANKED 0
+#define RT_SORT_RANKED 1
 #endif
 #ifndef RT_EXTEND_MIN_BLOCKS
 #define RT_EXTEND_MIN_BLOCKS 8  // 64 registers per thread -> 32 resident warps per SM

@@ -140,7 +140,7 @@ __device__ __forceinline__ bool work_to_pixel(const rt_frame& fr, unsigned long 
   if (fr.shard_mode == RT_SHARD_TILES) {
     uint32_t ts = fr.tile_size, ts2 = ts * ts;
     uint32_t k = (uint32_t)(pl / ts2), within = (uint32_t)(pl - (unsigned long long)k * ts2);
-    uint32_t tile = k * fr.shard_count + fr.shard_rank;
+    uint32_t tile = __ldg(fr.tile_list + k);  // which tiles a shard owns is the host's decision (plan_shard)
     uint32_t tx = tile % fr.tiles_x, ty = tile / fr.tiles_x;
     x = tx * ts + within % ts;
     y = ty * ts + within / ts;

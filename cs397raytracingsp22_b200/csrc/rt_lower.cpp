@@ -13,6 +13,7 @@
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
+#include <thread>
 #include <unordered_map>
 
 namespace rt {
@@ -165,7 +166,8 @@ bool sweep_split(std::vector<BPrim>& prims, uint32_t first, uint32_t count, floa
   return true;
 }
 
-void subdivide(std::vector<BPrim>& prims, std::vector<BNode>& nodes, uint32_t ni, uint32_t max_leaf) {
+// `recurse` false: split this node once (its two children are appended, their boxes are still unset) and stop
+void subdivide(std::vector<BPrim>& prims, std::vector<BNode>& nodes, uint32_t ni, uint32_t max_leaf, bool recurse = true) {
   const int NB = 16;
   uint32_t first = nodes[ni].leftFirst, count = nodes[ni].count;
   // bounds
@@ -205,8 +207,10 @@ void subdivide(std::vector<BPrim>& prims, std::vector<BNode>& nodes, uint32_t ni
     nodes[left + 1].count = first + count - mid;
     nodes[ni].leftFirst = left;
     nodes[ni].count = 0;
-    subdivide(prims, nodes, left, max_leaf);
-    subdivide(prims, nodes, left + 1, max_leaf);
+    if (recurse) {
+      subdivide(prims, nodes, left, max_leaf);
+      subdivide(prims, nodes, left + 1, max_leaf);
+    }
     return;
   }
 
@@ -313,11 +317,18 @@ void subdivide(std::vector<BPrim>& prims, std::vector<BNode>& nodes, uint32_t ni
   nodes[left + 1].count = first + count - mid;
   nodes[ni].leftFirst = left;
   nodes[ni].count = 0;
-  subdivide(prims, nodes, left, max_leaf);
-  subdivide(prims, nodes, left + 1, max_leaf);
+  if (recurse) {
+    subdivide(prims, nodes, left, max_leaf);
+    subdivide(prims, nodes, left + 1, max_leaf);
+  }
 }
 
 // nodes[0] = root, nodes[1] = padding so that child pairs start on even indices (64-byte pairs)
+// Big inputs are built in parallel (the reference's one-time BVH build, geometry.rs:175-217, is serial): the top of
+// the tree is split serially, largest node first, until there are kBuildTasks open subtrees; each subtree is then built
+// by its own thread into its own node array (the primitive ranges are disjoint) and spliced in.  The tree is the one
+// the serial build produces - same splits, same boxes - only the numbering of the nodes differs.
+const uint32_t kParallelMin = 8192, kBuildTasks = 16;
 void build_bvh(std::vector<BPrim>& prims, uint32_t max_leaf, std::vector<BNode>& nodes) {
   nodes.clear();
   nodes.reserve(2 * prims.size() + 2);
@@ -327,7 +338,54 @@ void build_bvh(std::vector<BPrim>& prims, uint32_t max_leaf, std::vector<BNode>&
   nodes.push_back(root);
   nodes.push_back(BNode{});
   for (int k = 0; k < 3; ++k) nodes[1].mn[k] = nodes[1].mx[k] = 0.0f;
-  if (!prims.empty()) subdivide(prims, nodes, 0, max_leaf);
+  if (prims.empty()) return;
+  const unsigned hw = std::thread::hardware_concurrency();
+  if (prims.size() < kParallelMin || hw < 2) {
+    subdivide(prims, nodes, 0, max_leaf);
+    return;
+  }
+  // phase 1: open subtrees, largest first
+  std::vector<uint32_t> open{0}, closed;
+  while (!open.empty() && open.size() + closed.size() < kBuildTasks) {
+    size_t bi = 0;
+    for (size_t i = 1; i < open.size(); ++i)
+      if (nodes[open[i]].count > nodes[open[bi]].count) bi = i;
+    const uint32_t ni = open[bi];
+    open.erase(open.begin() + bi);
+    if (nodes[ni].count < kParallelMin / 8) {  // small enough: finish it in phase 2 as it is
+      closed.push_back(ni);
+      continue;
+    }
+    subdivide(prims, nodes, ni, max_leaf, false);
+    if (nodes[ni].count == 0) {  // it was split: its children are open now
+      open.push_back(nodes[ni].leftFirst);
+      open.push_back(nodes[ni].leftFirst + 1);
+    }                            // else: it stays a leaf, done
+  }
+  closed.insert(closed.end(), open.begin(), open.end());
+  // phase 2: one thread per subtree, each into its own array (local node 0 = the subtree's root, 1 = padding)
+  std::vector<std::vector<BNode>> sub(closed.size());
+  std::vector<std::thread> workers;
+  for (size_t t = 0; t < closed.size(); ++t)
+    workers.emplace_back([&, t] {
+      sub[t].reserve(2 * (size_t)nodes[closed[t]].count + 2);
+      sub[t].push_back(nodes[closed[t]]);
+      sub[t].push_back(BNode{});
+      subdivide(prims, sub[t], 0, max_leaf);
+    });
+  for (auto& w : workers) w.join();
+  // phase 3: splice (local child indices start at 2)
+  for (size_t t = 0; t < closed.size(); ++t) {
+    const uint32_t base = (uint32_t)nodes.size();
+    for (size_t i = 2; i < sub[t].size(); ++i) {
+      BNode n = sub[t][i];
+      if (!n.count) n.leftFirst = n.leftFirst - 2 + base;
+      nodes.push_back(n);
+    }
+    BNode r = sub[t][0];
+    if (!r.count) r.leftFirst = r.leftFirst - 2 + base;
+    nodes[closed[t]] = r;
+  }
 }
 
 // Children per interior node: 2 (adjacent pairs, 64 B per fetch) or, with -DRT_BVH4=1, 4 (adjacent groups of four

@@ -104,6 +104,7 @@ struct rt_frame {
   uint32_t k0, k1;                  // Philox key
   // shard
   uint32_t shard_mode, shard_rank, shard_count, tile_size, tiles_x, tiles_y;
+  const uint32_t* tile_list;        // RT_SHARD_TILES: row-major tile ids of this shard, in the order it walks them (device pointer)
   uint32_t sample_begin, sample_count;
   uint32_t sample_major;            // 1: consecutive work indices walk the pixels (sample index changes slowest)
   unsigned long long pixel_slots;   // pixel slots of this shard (work items = pixel_slots * sample_count)

@@ -23,9 +23,15 @@ def sample_range(rank: int, world: int, begin: int, end: int) -> tuple[int, int]
 
 
 def tiles_of_rank(rank: int, world: int, width: int, height: int, tile: int = 64) -> list[tuple[int, int]]:
-    """Interleaved tiles (tile index % world == rank), row-major tile order — mirrors work_to_pixel()."""
+    """Tile (tx, ty) belongs to rank (tx + stride * ty) % world, stride = the smallest odd number >= 3 coprime to world:
+    diagonals, so that vertical structures of the scene do not line up with one rank's tiles.  Row-major order -
+    mirrors plan_shard() in csrc/rt_api.cu."""
+    import math
     tx, ty = (width + tile - 1) // tile, (height + tile - 1) // tile
-    return [(t % tx, t // tx) for t in range(rank, tx * ty, world)]
+    stride = 3
+    while math.gcd(stride, world) != 1:
+        stride += 2
+    return [(x, y) for y in range(ty) for x in range(tx) if (x + stride * y) % world == rank]
 
 
 def shard_opts(rank: int, world: int, seed: int, mode: str = "samples", tile: int = 64, sample_begin: int = 0,
