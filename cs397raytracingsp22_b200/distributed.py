@@ -11,6 +11,8 @@ torch is plumbing here (device memory, streams, torch.distributed); the renderin
 """
 from __future__ import annotations
 
+import math
+
 from . import _ffi
 
 
@@ -22,15 +24,20 @@ def sample_range(rank: int, world: int, begin: int, end: int) -> tuple[int, int]
     return b, b + base + (1 if rank < rem else 0)
 
 
-def tiles_of_rank(rank: int, world: int, width: int, height: int, tile: int = 64) -> list[tuple[int, int]]:
-    """Tile (tx, ty) belongs to rank (tx + stride * ty) % world, stride = the smallest odd number >= 3 coprime to world:
-    diagonals, so that vertical structures of the scene do not line up with one rank's tiles.  Row-major order -
-    mirrors plan_shard() in csrc/rt_api.cu."""
-    import math
-    tx, ty = (width + tile - 1) // tile, (height + tile - 1) // tile
+def tile_stride(world: int) -> int:
+    """The smallest odd number >= 3 coprime to `world` - mirrors plan_shard() in csrc/rt_api.cu."""
     stride = 3
     while math.gcd(stride, world) != 1:
         stride += 2
+    return stride
+
+
+def tiles_of_rank(rank: int, world: int, width: int, height: int, tile: int = 64) -> list[tuple[int, int]]:
+    """Tile (tx, ty) belongs to rank (tx + stride * ty) % world, stride = tile_stride(world): diagonals, so that
+    vertical structures of the scene do not line up with one rank's tiles.  Row-major order - mirrors plan_shard()
+    in csrc/rt_api.cu."""
+    tx, ty = (width + tile - 1) // tile, (height + tile - 1) // tile
+    stride = tile_stride(world)
     return [(x, y) for y in range(ty) for x in range(tx) if (x + stride * y) % world == rank]
 
 

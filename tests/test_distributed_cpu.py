@@ -63,3 +63,22 @@ def test_two_ranks_reduce_to_the_single_rank_accumulator():
 def test_reduce_is_a_no_op_without_a_process_group():
     acc = torch.arange(8, dtype=torch.int64)
     assert D.reduce_accum(acc) is acc
+
+
+
+@pytest.mark.parametrize("world,w,h,tile", [(2, 50, 37, 16), (3, 33, 20, 8), (8, 1920, 1080, 16)])
+def test_tile_shards_partition_the_frame(world, w, h, tile):
+    """Every tile (ragged ones at the right and bottom edges included) has exactly one owner, and no rank owns more
+    than its share plus one diagonal's worth - the host-side mirror of plan_shard() in csrc/rt_api.cu."""
+    tx, ty = (w + tile - 1) // tile, (h + tile - 1) // tile
+    seen = {}
+    for r in range(world):
+        for t in D.tiles_of_rank(r, world, w, h, tile):
+            assert t not in seen
+            seen[t] = r
+    assert len(seen) == tx * ty
+    counts = [sum(1 for v in seen.values() if v == r) for r in range(world)]
+    assert max(counts) - min(counts) <= max(tx, ty) // world + 1
+    # neighbours in a row and in a column belong to different ranks (diagonals, not columns or rows)
+    assert all(seen[(x, y)] != seen[(x + 1, y)] for y in range(ty) for x in range(tx - 1))
+    assert all(seen[(x, y)] != seen[(x, y + 1)] for y in range(ty - 1) for x in range(tx))
