@@ -18,7 +18,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.environ.get("RT_B200_LIB") or os.path.join(HERE, "librt_b200.so")  # RT_B200_LIB: A/B builds
 SOURCES = ["rt_kernels.cu", "rt_api.cu", "rt_lower.cpp", "rt_png.cpp", "rt_jpeg.cpp"]
-HEADERS = ["rt_kernels.h", "rt_lower.h", "rt_types.h", "rt_config.cuh", "rt_device_math.cuh", "rt_traverse.cuh", "rt_materials.cuh", os.path.join("..", "..", "include", "rt_b200.h")]
+HEADERS = ["rt_kernels.h", "rt_lower.h", "rt_types.h", "rt_config.cuh", "rt_device_math.cuh", "rt_traverse.cuh", "rt_materials.cuh", "rt_shade.cuh", os.path.join("..", "..", "include", "rt_b200.h")]
 
 
 def _nvcc() -> str:

@@ -51,7 +51,8 @@ struct rt_scene {
   bool lowered = false;
   bool committed = false;
   int device = -1;
-  DevBuf d_nodes, d_tris, d_shade, d_objects, d_mats, d_textures, d_texels, d_planes, d_guards, d_guard_list;
+  DevBuf d_geom;  // BVH nodes, then (256-byte aligned) triangle records: one range, so one L2 access-policy window covers both
+  DevBuf d_shade, d_objects, d_mats, d_textures, d_texels, d_planes, d_guards, d_guard_list;
   rt_dev_scene dev{};
 
   // wavefront engine state: ray queues, hit records, shade queues, sort buffers, control block
@@ -69,6 +70,7 @@ struct rt_scene {
   };
   Wavefront wf;
   cudaStream_t own_stream = nullptr;
+  size_t geom_bytes = 0;
   uint32_t sm_count = 148;
   uint32_t trace_blocks_per_sm = 8;  // resident blocks per SM of the persistent kernels (occupancy query)
   uint32_t path_blocks_per_sm = 6;
@@ -175,6 +177,52 @@ uint32_t persistent_grid(const rt_scene* s, uint32_t per_sm_default, uint32_t re
   uint32_t per_sm = requested ? std::min(requested, per_sm_default) : per_sm_default;
   return s->sm_count * std::max(1u, per_sm);
 }
+
+// RT_L2_PERSIST: while an engine runs, the BVH nodes and triangle records (one range, a few MB) are marked
+// "persisting" in L2 through the stream's access-policy window, so the ray queues streaming through L2 cannot evict
+// them.  The window is taken off the stream again when the engine returns (the stream may be the caller's).
+#ifndef RT_L2_PERSIST
+#define RT_L2_PERSIST 0
+#endif
+struct L2Window {
+  cudaStream_t st = nullptr;
+  bool on = false;
+  void open(const rt_scene* s, cudaStream_t stream) {
+#if RT_L2_PERSIST
+    if (!s->d_geom.p || !s->geom_bytes) return;
+    int max_persist = 0, max_window = 0;
+    cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, s->device);
+    cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, s->device);
+    size_t bytes = std::min<size_t>(s->geom_bytes, (size_t)std::max(0, max_window));
+    if (!bytes || !max_persist) return;
+    if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, std::min<size_t>(bytes, (size_t)max_persist)) != cudaSuccess) {
+      cudaGetLastError();
+      return;
+    }
+    cudaStreamAttrValue v{};
+    v.accessPolicyWindow.base_ptr = s->d_geom.p;
+    v.accessPolicyWindow.num_bytes = bytes;
+    v.accessPolicyWindow.hitRatio = bytes <= (size_t)max_persist ? 1.0f : (float)max_persist / (float)bytes;
+    v.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+    v.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+    if (cudaStreamSetAttribute(stream, cudaStreamAttributeAccessPolicyWindow, &v) != cudaSuccess) {
+      cudaGetLastError();
+      return;
+    }
+    st = stream;
+    on = true;
+#else
+    (void)s; (void)stream;
+#endif
+  }
+  ~L2Window() {
+    if (!on) return;
+    cudaStreamAttrValue v{};
+    v.accessPolicyWindow.num_bytes = 0;
+    cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &v);
+    cudaCtxResetPersistingL2Cache();
+  }
+};
 
 int ensure_wavefront(rt_scene* s, uint32_t capacity) {
   int rc = ensure_runtime(s);
@@ -390,6 +438,8 @@ int run_wavefront(rt_scene* s, const rt_frame& fr_in, unsigned long long total, 
   fr.capacity = std::max<uint32_t>(128u, (fr.capacity + 127u) / 128u * 128u);
   if ((rc = ensure_wavefront(s, fr.capacity)) != RT_OK) return rc;
   rt_scene::Wavefront& L = s->wf;
+  L2Window l2;
+  l2.open(s, st);
   const uint32_t grid = persistent_grid(s, s->trace_blocks_per_sm, blocks_per_sm);
   // Iterations are enqueued two at a time; after each pair the host asks for the control block's poll words and reads the
   // answer to the request before last, so two to four iterations are always queued ahead of the device and at most
@@ -523,6 +573,8 @@ int run_megakernel(rt_scene* s, const rt_frame& fr_in, unsigned long long total,
   rt_scene::Wavefront& L = s->wf;
   EventPair ev;
   if ((rc = ev.create()) != RT_OK) return rc;
+  L2Window l2;
+  l2.open(s, st);
   CUDA_TRY(cudaEventRecord(ev.a, st));
   rt::launch_init(L.ctrl, 0ull, total, st);
   rt::launch_path(s->dev, fr, L.ctrl, d_accum, total, persistent_grid(s, s->path_blocks_per_sm, blocks_per_sm), st);
@@ -689,7 +741,7 @@ void rt_scene_destroy(rt_scene* s) {
   if (s->device >= 0 && cudaSetDevice(s->device) == cudaSuccess) {
     unpin_lowered(s);
     free_wavefront(s);
-    free_buf(s->d_nodes); free_buf(s->d_tris); free_buf(s->d_shade); free_buf(s->d_objects);
+    free_buf(s->d_geom); free_buf(s->d_shade); free_buf(s->d_objects);
     free_buf(s->d_mats); free_buf(s->d_textures); free_buf(s->d_texels); free_buf(s->d_planes); free_buf(s->d_guards); free_buf(s->d_guard_list);
     free_buf(s->d_accum); free_buf(s->d_linear); free_buf(s->d_rgb8); free_buf(s->d_dbg);
     for (auto& b : s->d_tree) free_buf(b);
@@ -856,8 +908,11 @@ int rt_scene_upload(rt_scene* s) try {
   int rc;
   cudaStream_t st = 0;
   pin_lowered(s);
-  if ((rc = upload(s->d_nodes, L.nodes.data(), L.nodes.size() * 16, st)) != RT_OK) return rc;
-  if ((rc = upload(s->d_tris, L.tris.data(), L.tris.size() * 16, st)) != RT_OK) return rc;
+  const size_t node_bytes = (L.nodes.size() * 16 + 255) / 256 * 256, tri_bytes = L.tris.size() * 16;
+  if ((rc = ensure_buf(s->d_geom, node_bytes + tri_bytes)) != RT_OK) return rc;
+  s->geom_bytes = node_bytes + tri_bytes;
+  if (!L.nodes.empty()) CUDA_TRY(cudaMemcpyAsync(s->d_geom.p, L.nodes.data(), L.nodes.size() * 16, cudaMemcpyHostToDevice, st));
+  if (tri_bytes) CUDA_TRY(cudaMemcpyAsync((char*)s->d_geom.p + node_bytes, L.tris.data(), tri_bytes, cudaMemcpyHostToDevice, st));
   if ((rc = upload(s->d_shade, L.shade.data(), L.shade.size() * 16, st)) != RT_OK) return rc;
   if ((rc = upload(s->d_objects, L.objects.data(), L.objects.size() * 16, st)) != RT_OK) return rc;
   if ((rc = upload(s->d_mats, L.mats.data(), L.mats.size() * 16, st)) != RT_OK) return rc;
@@ -868,7 +923,7 @@ int rt_scene_upload(rt_scene* s) try {
   if ((rc = upload(s->d_guard_list, L.guard_list.data(), L.guard_list.size() * 4, st)) != RT_OK) return rc;
   CUDA_TRY(cudaStreamSynchronize(st));
   rt_dev_scene& d = s->dev;
-  d.nodes = s->d_nodes.p; d.tris = s->d_tris.p; d.shade = s->d_shade.p; d.objects = s->d_objects.p;
+  d.nodes = s->d_geom.p; d.tris = (char*)s->d_geom.p + node_bytes; d.shade = s->d_shade.p; d.objects = s->d_objects.p;
   d.mats = s->d_mats.p; d.textures = s->d_textures.p; d.texels = s->d_texels.p; d.planes = s->d_planes.p; d.guards = s->d_guards.p; d.guard_list = s->d_guard_list.p;
   d.tlas_root = L.tlas_root;
   d.tlas_base = L.tlas_base;

@@ -9,7 +9,7 @@
 #ifndef RT_SMEM_STACK
 #define RT_SMEM_STACK 16   // traversal-stack entries per thread kept in shared memory
 #endif
-#define RT_LOCAL_STACK 48  // overflow entries (local memory; host checks depth <= 62)
+#define RT_LOCAL_STACK (64 - RT_SMEM_STACK)  // overflow entries (local memory; 64 in all, the host checks depth <= 62)
 // RT_STREAM_HINTS: ray queue / hit record traffic uses the streaming (evict-first) cache operators so that it does
 // not push BVH nodes, triangles and texels out of L1/L2.  (Tried and dropped, profiles/r1_notes.md B2, B6: stack
 // entries that carry their entry distance, and prefetching the children of the pushed child.)

@@ -34,6 +34,35 @@ __device__ __forceinline__ float clampf(float v, float lo, float hi) { return v 
 __device__ __forceinline__ float4 ldq(const void* base, uint32_t quad) {
   return __ldg(reinterpret_cast<const float4*>(base) + quad);
 }
+// Cache-hinted variants for the two record streams of the traversal loop (compile-time experiments, both off:
+// see profiles/r2_notes.md C7).  RT_NODE_EVICT_LAST: BVH nodes ask L1 to keep them longest; RT_TRI_NO_ALLOC:
+// triangle records (rarely reused) do not allocate in L1.
+#ifndef RT_NODE_EVICT_LAST
+#define RT_NODE_EVICT_LAST 0
+#endif
+#ifndef RT_TRI_NO_ALLOC
+#define RT_TRI_NO_ALLOC 0
+#endif
+__device__ __forceinline__ float4 ldq_node(const float4* p) {
+#if RT_NODE_EVICT_LAST
+  float4 v;
+  asm("ld.global.nc.L1::evict_last.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+  return v;
+#else
+  return __ldg(p);
+#endif
+}
+__device__ __forceinline__ float4 ldq_tri(const void* base, uint32_t quad) {
+#if RT_TRI_NO_ALLOC
+  float4 v;
+  asm("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];"
+      : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+      : "l"(reinterpret_cast<const float4*>(base) + quad));
+  return v;
+#else
+  return __ldg(reinterpret_cast<const float4*>(base) + quad);
+#endif
+}
 __device__ __forceinline__ uint32_t fbits(float f) { return __float_as_uint(f); }
 
 // ------------------------------------------------------------------ RNG contract

@@ -287,7 +287,7 @@ __device__ __forceinline__ void trav_interior(const rt_dev_scene& sc, Trav& T) {
 #endif
   {
     const float4* pair = reinterpret_cast<const float4*>(sc.nodes) + (size_t)e * 2u;
-    l0 = __ldg(pair); l1 = __ldg(pair + 1); r0 = __ldg(pair + 2); r1 = __ldg(pair + 3);
+    l0 = ldq_node(pair); l1 = ldq_node(pair + 1); r0 = ldq_node(pair + 2); r1 = ldq_node(pair + 3);
   }
   if (COUNT) {
     T.cnt.nodes += 2;
@@ -320,7 +320,7 @@ __device__ __forceinline__ void trav_leaf(const rt_dev_scene& sc, Trav& T) {
     const f3 o = T.o, d = T.d;
     for (uint32_t k = 0; k < n; ++k) {
       uint32_t q = (first + k) * RT_TRI_QUADS;
-      float4 a0 = ldq(sc.tris, q), a1 = ldq(sc.tris, q + 1), a2 = ldq(sc.tris, q + 2);
+      float4 a0 = ldq_tri(sc.tris, q), a1 = ldq_tri(sc.tris, q + 1), a2 = ldq_tri(sc.tris, q + 2);
       if (COUNT) T.cnt.tris += 1;
       f3 va = mk(a0.x, a0.y, a0.z), e1 = mk(a0.w, a1.x, a1.y), e2 = mk(a1.z, a1.w, a2.x);
       f3 qv = cross(d, e2);

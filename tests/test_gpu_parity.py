@@ -172,13 +172,15 @@ def test_low_spp_images_track_the_oracle_sample_for_sample(gpu, small_scenes, na
     assert st_g.rays <= st_o.rays * 1.001 and st_g.rays >= 0.9 * st_o.rays
     diff = np.abs(lin_g - lin_o)
     scale = max(float(lin_o.mean()), 1e-6)
-    assert np.median(diff) <= 1e-5 * max(scale, 1.0)
+    assert np.median(diff) <= 1e-9 * max(scale, 1.0)
+    # measured on B200 (tools/parity_margins.py, profiles/r2_parity_margins.log): no decorrelated pixel on c1-c3 and c5,
+    # 7e-5 of the pixels on c4; the bars leave an order of magnitude
     bad = (diff.max(axis=2) > 1e-3 * np.maximum(lin_o.max(axis=2), scale)).mean()
-    assert bad < 0.03, f"{name}: {bad:.4f} of pixels decorrelated"
-    assert abs(float(lin_g.mean()) - float(lin_o.mean())) <= 2e-3 * scale
+    assert bad < 1e-3, f"{name}: {bad:.5f} of pixels decorrelated"
+    assert abs(float(lin_g.mean()) - float(lin_o.mean())) <= 1e-5 * scale
     # 8-bit output: identical except where the linear value sits on a quantisation edge or the pixel decorrelated
     d8 = np.abs(rgb_g.astype(np.int32) - rgb_o.astype(np.int32)).max(axis=2)
-    assert (d8 <= 1).mean() > 0.97
+    assert d8.max() <= 1 and (d8 == 0).mean() > 0.999
 
 
 @pytest.mark.parametrize("name,kw", [("c1", dict(width=48, height=48, spp=1024)),
@@ -188,7 +190,10 @@ def test_low_spp_images_track_the_oracle_sample_for_sample(gpu, small_scenes, na
                                      ("c5", dict(width=64, height=36, spp=1024, map_size=128, grid=6))])
 def test_converged_images_rmse(gpu, small_scenes, name, kw):
     """>= 1024 spp, reduced resolution (so the CPU side takes seconds): RMSE in linear radiance, relative to the mean
-    radiance, must be < 0.5 % and PSNR (peak = 1.0) > 50 dB; the u8 images agree within 1 LSB on > 99 % of pixels."""
+    radiance, must be < 1e-4 and PSNR (peak = 1.0) > 95 dB; the u8 images never differ by more than 1 LSB and are
+    identical on > 99.5 % of the pixels.  (Measured, profiles/r2_parity_margins.log: relative RMSE 3e-7 ... 1e-5, PSNR
+    112 ... 139 dB, u8 identical on >= 99.96 %: with shared Philox keys the two sides compute the same samples, and what
+    is left is libm ulps and the rare path whose discrete decision an ulp flips.)"""
     sc = small_scenes(name, **kw)
     lin_g, rgb_g, st_g, lin_o, rgb_o, st_o = _render_pair(sc)
     finite = np.isfinite(lin_o).all(axis=2) & np.isfinite(lin_g).all(axis=2)
@@ -198,10 +203,10 @@ def test_converged_images_rmse(gpu, small_scenes, name, kw):
     mean = float(lin_o[finite].mean())
     psnr = 10 * math.log10(1.0 / max(rmse ** 2, 1e-20))
     print(f"{name}: rmse {rmse:.3e}  mean radiance {mean:.4f}  rel {rmse / mean:.3e}  psnr {psnr:.1f} dB")
-    assert rmse <= 5e-3 * mean
-    assert psnr > 50.0
+    assert rmse <= 1e-4 * mean
+    assert psnr > 95.0
     d8 = np.abs(rgb_g.astype(np.int32) - rgb_o.astype(np.int32)).max(axis=2)
-    assert (d8 <= 1).mean() > 0.99
+    assert d8.max() <= 1 and (d8 == 0).mean() > 0.995
 
 
 def _debug_mode_scene(width=128, height=72, spp=4):
