@@ -49,6 +49,29 @@
 #ifndef RT_SORT_RANKED
 #define RT_SORT_RANKED 1
 #endif
+// Children per interior node come before this switch: with the binary tree, how a child pair is stored.
+//   0: (min, max) per child, four 128-bit fetches per visit, slab test = 12 FFMA + 20 FMNMX(3)
+//   1: (centre, half extent) per child, four fetches, slab test = 18 FFMA + 8 FMNMX(3) (see slab_ch(), rt_traverse.cuh)
+//   2: packed pair - two centres with their links, six half extents as bf16 (rounded up) - THREE fetches per visit;
+//      the fourth quad of the 64-byte slot is never read.
+// Measured (profiles/r2_notes.md C9): every extra 128-bit fetch per visit costs k_trace 6-9 % (the visit sits at the
+// knee of the L1 data pipe: 4 wavefronts per LDG.128 whatever the number of active lanes), six ALU instructions
+// fewer per visit are worth 0.6 %; the packed pair is worth 1.1 % of k_trace on C4 and 2.8 % on C5 for 1 % more node
+// visits (bf16 inflates a box by < 0.8 % of its half extent).  rt_lower.cpp is compiled with the same switch (one nvcc
+// command).  The 4-wide tree keeps (min, max).
+#ifndef RT_NODE_CH
+#if RT_BVH4
+#define RT_NODE_CH 0
+#else
+#define RT_NODE_CH 2
+#endif
+#endif
+#if RT_NODE_CH && RT_BVH4
+#error "RT_NODE_CH is implemented for the binary tree only"
+#endif
+#ifndef RT_EXTRA_LDG
+#define RT_EXTRA_LDG 0  // diagnostic: extra node fetches per visit (rt_traverse.cuh)
+#endif
 #ifndef RT_EXTEND_MIN_BLOCKS
 #define RT_EXTEND_MIN_BLOCKS 8  // 64 registers per thread -> 32 resident warps per SM
 #endif

@@ -393,6 +393,13 @@ void build_bvh(std::vector<BPrim>& prims, uint32_t max_leaf, std::vector<BNode>&
 #ifndef RT_BVH4
 #define RT_BVH4 0
 #endif
+#ifndef RT_NODE_CH  // how a child pair is stored: see rt_config.cuh (same default here)
+#if RT_BVH4
+#define RT_NODE_CH 0
+#else
+#define RT_NODE_CH 2
+#endif
+#endif
 const uint32_t kWidth = RT_BVH4 ? 4u : 2u;
 const uint32_t kNoChild = 0xFFFFFFFFu;  // link of an unused slot of a 4-wide group (count == 0)
 inline bool empty_slot(const BNode& n) { return n.count == 0 && n.leftFirst == kNoChild; }
@@ -938,6 +945,59 @@ int lower_scene(const std::vector<HostTexture>& textures, const std::vector<rt_m
   // final form of the link word: the packed traversal entry (leaf flag | first << 4 | count, or the
   // index of the child pair), so the kernel uses lo.w as is; hi.w keeps the plain count
   for (size_t q = 0; q < L.nodes.size(); q += 2) L.nodes[q].u[3] = pack_entry(L.nodes[q].u[3], L.nodes[q + 1].u[3]);
+#if RT_NODE_CH
+  // (min, max) -> (centre, half extent), the half extent rounded up so that [c - h, c + h] contains [min, max]
+  auto to_ch = [](float lo, float hi, float& c, float& h) {
+    if (!(lo <= hi) || !std::isfinite(lo) || !std::isfinite(hi)) {  // empty slot: can never be hit
+      c = 0.0f;
+      h = -1.0f;
+      return;
+    }
+    c = 0.5f * lo + 0.5f * hi;
+    const double need = std::max((double)hi - (double)c, (double)c - (double)lo);
+    h = (float)need;
+    if ((double)h < need) h = std::nextafter(h, INFINITY);
+  };
+#if RT_NODE_CH == 2
+  // packed child pairs: quad 0 = (left centre, left link), quad 1 = (right centre, right link), quad 2 = the six half
+  // extents as bf16, rounded up; quad 3 of the 64-byte slot is never fetched (the plain counts stay there)
+  auto bf16_up = [](float h) -> uint32_t {
+    uint32_t b;
+    std::memcpy(&b, &h, 4);
+    if (h > 0.0f && (b & 0xFFFFu)) b = (b | 0xFFFFu) + 1u;  // next bf16 above (carries into the exponent as it should)
+    return b >> 16;
+  };
+  for (size_t q = 0; q + 3 < L.nodes.size(); q += 4) {
+    float c[2][3], h[2][3];
+    for (int s = 0; s < 2; ++s)
+      for (int k = 0; k < 3; ++k) to_ch(L.nodes[q + 2 * s].f[k], L.nodes[q + 2 * s + 1].f[k], c[s][k], h[s][k]);
+    const uint32_t link_l = L.nodes[q].u[3], link_r = L.nodes[q + 2].u[3];
+    const uint32_t count_l = L.nodes[q + 1].u[3], count_r = L.nodes[q + 3].u[3];
+    Quad q0, q1, q2, q3;
+    for (int k = 0; k < 3; ++k) {
+      q0.f[k] = c[0][k];
+      q1.f[k] = c[1][k];
+    }
+    q0.u[3] = link_l;
+    q1.u[3] = link_r;
+    const uint32_t hb[6] = {bf16_up(h[0][0]), bf16_up(h[0][1]), bf16_up(h[0][2]), bf16_up(h[1][0]), bf16_up(h[1][1]), bf16_up(h[1][2])};
+    q2.u[0] = hb[0] | (hb[1] << 16);
+    q2.u[1] = hb[2] | (hb[3] << 16);
+    q2.u[2] = hb[4] | (hb[5] << 16);
+    q2.u[3] = 0;
+    q3.u[0] = count_l; q3.u[1] = count_r; q3.u[2] = q3.u[3] = 0;
+    L.nodes[q] = q0; L.nodes[q + 1] = q1; L.nodes[q + 2] = q2; L.nodes[q + 3] = q3;
+  }
+#else
+  for (size_t q = 0; q < L.nodes.size(); q += 2)
+    for (int k = 0; k < 3; ++k) {
+      float c, h;
+      to_ch(L.nodes[q].f[k], L.nodes[q + 1].f[k], c, h);
+      L.nodes[q].f[k] = c;
+      L.nodes[q + 1].f[k] = h;
+    }
+#endif
+#endif
   return RT_OK;
 }
 

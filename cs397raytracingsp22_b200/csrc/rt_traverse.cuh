@@ -38,6 +38,23 @@ __device__ __forceinline__ bool slab(float4 lo, float4 hi, f3 inv, f3 oi, float 
   tn = a;
   return a <= b * 1.0000005f;
 }
+#if RT_NODE_CH
+// The same test on a box stored as (centre, half extent): per axis the distance to the centre plane, m = c*inv + oi,
+// and the half width of the slab along the ray, e = h*|inv|, give near = m - e and far = m + e without a min / max
+// pair - three FFMAs per axis instead of two FFMAs and two FMNMXs, i.e. the work moves from the ALU pipe (the busiest
+// pipe of k_trace) to the FMA pipe and six instructions per child pair disappear.  Conservative like slab(): the
+// lowering rounds h up so that [c - h, c + h] contains the padded box.
+template <class V>
+__device__ __forceinline__ bool slab_ch(float4 c, V h, f3 inv, f3 ainv, f3 oi, float tmin, float tmax, float& tn) {
+  float mx = __fmaf_rn(c.x, inv.x, oi.x), my = __fmaf_rn(c.y, inv.y, oi.y), mz = __fmaf_rn(c.z, inv.z, oi.z);
+  float nx = __fmaf_rn(-h.x, ainv.x, mx), ny = __fmaf_rn(-h.y, ainv.y, my), nz = __fmaf_rn(-h.z, ainv.z, mz);
+  float fx = __fmaf_rn(h.x, ainv.x, mx), fy = __fmaf_rn(h.y, ainv.y, my), fz = __fmaf_rn(h.z, ainv.z, mz);
+  float a = fmaxf(fmaxf(nx, ny), fmaxf(nz, tmin));
+  float b = fminf(fminf(fx, fy), fminf(fz, tmax));
+  tn = a;
+  return a <= b * 1.0000005f;
+}
+#endif
 // reciprocal direction for the slab tests only.  A component that is exactly (or nearly) zero is
 // replaced by +-1e-20 so that lo*inv + oi never becomes inf - inf: the slab then yields two huge
 // finite values of the right signs and does not constrain the interval, which is what a ray
@@ -78,6 +95,9 @@ struct Trav {
   const float4* qC;
   uint32_t slot;
   f3 o, d, inv, oi; // current-space ray (world or instance), reciprocal direction, -o*inv
+#if RT_NODE_CH
+  f3 ainv;          // |inv|
+#endif
   float t_min, t_max;
   float ray_t_max;  // the ray's own upper limit (t_max is temporarily replaced during a volume boundary query)
   uint32_t entry;   // packed node link being visited, RT_ENTRY_NONE when a pop is needed
@@ -117,6 +137,9 @@ struct Trav {
     o = no; d = nd;
     inv = approx_inv(d);
     oi = mk(-o.x * inv.x, -o.y * inv.y, -o.z * inv.z);
+#if RT_NODE_CH
+    ainv = mk(fabsf(inv.x), fabsf(inv.y), fabsf(inv.z));
+#endif
   }
   // the world-space reciprocal direction survives an instance visit in shared memory (cheaper than 3 reciprocals)
   __device__ __forceinline__ void save_world_inv() const {
@@ -130,6 +153,9 @@ struct Trav {
     for (int k = 0; k < 6; ++k) asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v[k]) : "r"(wbase + k * (RT_BLOCK * 4u)) : "memory");
     inv = mk(v[0], v[1], v[2]);
     oi = mk(v[3], v[4], v[5]);
+#if RT_NODE_CH
+    ainv = mk(fabsf(inv.x), fabsf(inv.y), fabsf(inv.z));
+#endif
   }
   // mesh-bounded volume: the closest hit found so far and t_entr wait in shared memory while the boundary queries run
   __device__ __forceinline__ void vol_save(const Best& b, float t_entr) const {
@@ -287,15 +313,45 @@ __device__ __forceinline__ void trav_interior(const rt_dev_scene& sc, Trav& T) {
 #endif
   {
     const float4* pair = reinterpret_cast<const float4*>(sc.nodes) + (size_t)e * 2u;
-    l0 = ldq_node(pair); l1 = ldq_node(pair + 1); r0 = ldq_node(pair + 2); r1 = ldq_node(pair + 3);
+    l0 = ldq_node(pair); l1 = ldq_node(pair + 1); r0 = ldq_node(pair + 2);
+#if RT_NODE_CH != 2
+    r1 = ldq_node(pair + 3);
+#endif
   }
   if (COUNT) {
     T.cnt.nodes += 2;
     if (!T.in_blas) T.cnt.tlas_nodes += 2;
   }
+#if RT_EXTRA_LDG
+  // diagnostic only (profiles/r2_notes.md C9): RT_EXTRA_LDG more 128-bit fetches per visit, of the adjacent child pair
+  // (the triangle array follows the nodes in the same allocation, so the last pair's neighbour is readable) - no extra arithmetic - to see whether the visit is bound by L1 data-pipe wavefronts
+  {
+    const float4* pair = reinterpret_cast<const float4*>(sc.nodes) + (size_t)e * 2u;
+#pragma unroll
+    for (int k = 0; k < RT_EXTRA_LDG; ++k) {
+      float4 x;
+      asm volatile("ld.global.nc.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(x.x), "=f"(x.y), "=f"(x.z), "=f"(x.w) : "l"(pair + 4 + k));  // the NEXT pair (other addresses would be merged with the real loads)
+      if (fbits(x.x) == 0x7fc12345u) T.t_min = x.y + x.z + x.w;  // never true: keeps all four words of the load alive
+    }
+  }
+#endif
   float tl, tr;
+#if RT_NODE_CH == 2
+  // packed pair: l0 = (left centre, left link), l1 = (right centre, right link), r0 = the six half extents as bf16
+  // (rounded up by the lowering); the fourth quad of the 64-byte slot is not fetched
+  const uint32_t w0 = fbits(r0.x), w1 = fbits(r0.y), w2 = fbits(r0.z);
+  const f3 hL = mk(__uint_as_float(w0 << 16), __uint_as_float(w0 & 0xFFFF0000u), __uint_as_float(w1 << 16));
+  const f3 hR = mk(__uint_as_float(w1 & 0xFFFF0000u), __uint_as_float(w2 << 16), __uint_as_float(w2 & 0xFFFF0000u));
+  bool hl = slab_ch(l0, hL, T.inv, T.ainv, T.oi, T.t_min, T.best.t, tl);
+  bool hr = slab_ch(l1, hR, T.inv, T.ainv, T.oi, T.t_min, T.best.t, tr);
+  r0.w = l1.w;  // the right child's link, where the code below expects it
+#elif RT_NODE_CH
+  bool hl = slab_ch(l0, l1, T.inv, T.ainv, T.oi, T.t_min, T.best.t, tl);
+  bool hr = slab_ch(r0, r1, T.inv, T.ainv, T.oi, T.t_min, T.best.t, tr);
+#else
   bool hl = slab(l0, l1, T.inv, T.oi, T.t_min, T.best.t, tl);
   bool hr = slab(r0, r1, T.inv, T.oi, T.t_min, T.best.t, tr);
+#endif
   uint32_t el = fbits(l0.w), er = fbits(r0.w);
   if (hl && hr) {
     bool lfirst = tl <= tr;

@@ -16,6 +16,9 @@ METRICS = [
     "lts__t_sectors.sum", "lts__t_sectors.sum.per_second", "lts__throughput.avg.pct_of_peak_sustained_elapsed",
     "lts__t_sector_op_read_hit_rate.pct", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
     "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active",
+    "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active",
+    "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active", "l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed",
+    "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum", "l1tex__data_pipe_lsu_wavefronts.sum",
 ]
 STALLS = ["long_scoreboard", "wait", "barrier", "not_selected", "math_pipe_throttle", "branch_resolving", "short_scoreboard",
           "no_instruction", "dispatch_stall", "lg_throttle", "mio_throttle", "tex_throttle", "membar", "sleeping", "selected"]
