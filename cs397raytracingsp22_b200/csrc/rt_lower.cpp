@@ -948,9 +948,14 @@ int lower_scene(const std::vector<HostTexture>& textures, const std::vector<rt_m
 #if RT_NODE_CH
   // (min, max) -> (centre, half extent), the half extent rounded up so that [c - h, c + h] contains [min, max]
   auto to_ch = [](float lo, float hi, float& c, float& h) {
-    if (!(lo <= hi) || !std::isfinite(lo) || !std::isfinite(hi)) {  // empty slot: can never be hit
+    if (!(lo <= hi)) {  // empty or NaN slot: can never be hit
       c = 0.0f;
       h = -1.0f;
+      return;
+    }
+    if (!std::isfinite(lo) || !std::isfinite(hi)) {  // unbounded along this axis: never culls
+      c = 0.0f;
+      h = INFINITY;
       return;
     }
     c = 0.5f * lo + 0.5f * hi;
