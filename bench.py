@@ -527,7 +527,7 @@ def main():
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": workload_config(args, job.sc, job.desc),
         "engine": "megakernel" if megakernel else "wavefront",
-        "wavefront": int(args.wavefront or (1 << 24)), "scene_build_s": job.build_s, "scene_bytes": int(job.g.device_bytes()),
+        "wavefront": int(args.wavefront or (1 << 25)), "scene_build_s": job.build_s, "scene_bytes": int(job.g.device_bytes()),
         "rays_per_sec_M": rays_M, "rays_per_sample": job_rays / max(job_samples, 1),
         "gpu_launches": int(job_launches),
         "clocks": clock_info,

@@ -395,8 +395,11 @@ int plan_shard(const rt_camera& cam, const rt_render_opts& o, rt_frame& fr, unsi
 
 // paths in flight.  Every k_trace launch ends with a tail in which the last, longest ray batches finish on a nearly
 // empty machine (~125 us on C4, independent of the width), so wider is better: 1 M -> 1250, 2 M -> 1574, 4 M -> 1795,
-// 8 M -> 1903 Msamples/s.  140 bytes of state per path.
-const uint32_t kDefaultWavefront = 1u << 24;
+// 8 M -> 1903 Msamples/s in round 1; on the final kernels 16 Mi -> 2684, 32 Mi -> 2732, 64 Mi -> 2735 Msamples/s on a
+// whole C4 frame, 104.3 -> 100.3 ms on one eighth of it, C5 1763 -> 1796 (profiles/r2_notes.md C11).  148 bytes of
+// state per path: 32 Mi paths are 5 GB of a B200's 180 GB.  If that cannot be allocated the default is halved until it
+// can (a width the caller asked for is taken as given).
+const uint32_t kDefaultWavefront = 1u << 25;
 
 uint32_t pick_capacity(unsigned long long total, uint32_t requested) {
   unsigned long long cap = requested ? requested : kDefaultWavefront;
@@ -431,12 +434,17 @@ void stats_from_ctrl(const rt_ctrl& c, rt_stats* stats) {
 // The wavefront loop.  Launches are asynchronous; the device decides how many rays each iteration has.  The host
 // only peeks at a `done` flag every few iterations, two polls deep, so the stream never drains.
 int run_wavefront(rt_scene* s, const rt_frame& fr_in, unsigned long long total, long long* d_accum, bool count,
-                  bool use_events, cudaStream_t st, uint32_t blocks_per_sm, rt_stats* stats) {
+                  bool use_events, cudaStream_t st, uint32_t blocks_per_sm, bool capacity_is_default, rt_stats* stats) {
   int rc;
   rt_frame fr = fr_in;
   if (fr.phong) fr.sort_enabled = 0;  // camera ray + shadow ray pairs: slot i of the shadow pass belongs to slot i of the camera pass
   fr.capacity = std::max<uint32_t>(128u, (fr.capacity + 127u) / 128u * 128u);
-  if ((rc = ensure_wavefront(s, fr.capacity)) != RT_OK) return rc;
+  while ((rc = ensure_wavefront(s, fr.capacity)) != RT_OK) {
+    if (!capacity_is_default || fr.capacity <= (1u << 20)) return rc;
+    cudaGetLastError();  // out of memory for the default width: try half of it
+    free_wavefront(s);
+    fr.capacity = std::max<uint32_t>(128u, (fr.capacity / 2u + 127u) / 128u * 128u);
+  }
   rt_scene::Wavefront& L = s->wf;
   L2Window l2;
   l2.open(s, st);
@@ -1067,7 +1075,7 @@ int rt_render_accum(rt_scene* s, const rt_camera* cam, const rt_render_opts* opt
   }
   if (engine == RT_ENGINE_MEGAKERNEL) return run_megakernel(s, fr, total, (long long*)d_accum, st, o.blocks_per_sm, stats);
   return run_wavefront(s, fr, total, (long long*)d_accum, counters, (o.flags & RT_OPT_NO_EVENTS) == 0, st, o.blocks_per_sm,
-                       stats);
+                       o.wavefront == 0, stats);
 }
 RT_CATCH("rt_render_accum")
 

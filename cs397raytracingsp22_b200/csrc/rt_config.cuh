@@ -2,12 +2,18 @@
 #ifndef RT_CONFIG_CUH
 #define RT_CONFIG_CUH
 
+// Threads per block of the ray kernels (k_raygen, k_trace, k_shade, k_path, ...).  Measured at the same number of
+// resident warps per SM (profiles/r2_notes.md C11): 64 / 128 / 256 threads -> C4 2557 / 2658 / 2677, C3 984 / 1080 /
+// 1101 Msamples/s (k_shade pays one atomic on the queue cursor and two barriers per block; a bigger block halves the
+// atomics, and k_trace does not care).
 #ifndef RT_BLOCK
-#define RT_BLOCK 128
+#define RT_BLOCK 256
 #endif
 #define RT_WARPS (RT_BLOCK / 32)
+// Traversal-stack entries per thread kept in shared memory; deeper entries live in local memory (L1).  16 entries
+// meant a 100 KB carve-out; 4 entries (64 KB) leave L1 36 KB more and are worth 0.4-0.6 % (profiles/r2_notes.md C7, C11).
 #ifndef RT_SMEM_STACK
-#define RT_SMEM_STACK 16   // traversal-stack entries per thread kept in shared memory
+#define RT_SMEM_STACK 4
 #endif
 #define RT_LOCAL_STACK (64 - RT_SMEM_STACK)  // overflow entries (local memory; 64 in all, the host checks depth <= 62)
 // RT_STREAM_HINTS: ray queue / hit record traffic uses the streaming (evict-first) cache operators so that it does
@@ -73,7 +79,7 @@
 #define RT_EXTRA_LDG 0  // diagnostic: extra node fetches per visit (rt_traverse.cuh)
 #endif
 #ifndef RT_EXTEND_MIN_BLOCKS
-#define RT_EXTEND_MIN_BLOCKS 8  // 64 registers per thread -> 32 resident warps per SM
+#define RT_EXTEND_MIN_BLOCKS (1024 / RT_BLOCK)  // 64 registers per thread -> 32 resident warps per SM
 #endif
 
 #endif

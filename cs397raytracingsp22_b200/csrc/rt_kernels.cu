@@ -269,10 +269,10 @@ __global__ void __launch_bounds__(RT_BLOCK) k_surface(rt_dev_scene sc, rt_ctrl* 
 }
 
 // ------------------------------------------------------------------ k_shade
-// k_shade is latency bound on its gathers: 10 resident blocks (48 registers, ~100 B of spills) beat 7 blocks
+// k_shade is latency bound on its gathers: 40 resident warps (48 registers, ~100 B of spills) beat 28 warps
 // (72 registers, no spills) by 1 % on C4 and 7-10 % on the closed scenes C1 / C3 where shading dominates
 #ifndef RT_SHADE_MIN_BLOCKS
-#define RT_SHADE_MIN_BLOCKS 10
+#define RT_SHADE_MIN_BLOCKS (1280 / RT_BLOCK)  // 40 resident warps per SM
 #endif
 #ifndef RT_SHADE_WARP_SCAN
 #define RT_SHADE_WARP_SCAN 1
@@ -354,17 +354,31 @@ __global__ void __launch_bounds__(RT_BLOCK, RT_SHADE_MIN_BLOCKS) k_shade(rt_dev_
     if (oct == k) my_bal = bk;
   }
   __syncthreads();
-#if RT_WARPS == 4 && RT_SHADE_WARP_SCAN
-  if (warp == 0) {  // the 8 x 4 counters are exactly one warp's worth: exclusive prefix by shuffles, octant-major
+#if RT_SHADE_WARP_SCAN
+  if (warp == 0) {  // exclusive prefix of the 8 x RT_WARPS counters (octant-major) by one warp: each lane sums its run
+                    // of consecutive counters, the lane sums are scanned with shuffles, each lane writes its run back
+    constexpr int N = 8 * RT_WARPS, PER = (N + 31) / 32;
     uint32_t* cnt = &s_ocount[0][0];
-    const uint32_t c = cnt[lane];
-    uint32_t inc = c;
+    uint32_t c[PER], run = 0;
+#pragma unroll
+    for (int k = 0; k < PER; ++k) {
+      const int i = (int)lane * PER + k;
+      c[k] = i < N ? cnt[i] : 0u;
+      run += c[k];
+    }
+    uint32_t inc = run;
 #pragma unroll
     for (int off = 1; off < 32; off <<= 1) {
       uint32_t t = __shfl_up_sync(0xFFFFFFFFu, inc, off);
       if (lane >= (uint32_t)off) inc += t;
     }
-    cnt[lane] = inc - c;
+    uint32_t base = inc - run;
+#pragma unroll
+    for (int k = 0; k < PER; ++k) {
+      const int i = (int)lane * PER + k;
+      if (i < N) cnt[i] = base;
+      base += c[k];
+    }
     if (lane == 31) s_base = inc ? atomicAdd(&ctrl->n_next, inc) : 0u;
   }
 #else
@@ -442,7 +456,7 @@ __global__ void __launch_bounds__(RT_BLOCK, RT_SHADE_MIN_BLOCKS) k_shade(rt_dev_
 // at least 8 lanes are idle is within noise of refilling at once on C4 and happens to steer ptxas away from ~100 B of
 // spills in the traversal loop, which alone is worth 20 % (same source, RT_PATH_REGEN_MIN 1 vs 8).
 #ifndef RT_PATH_MIN_BLOCKS
-#define RT_PATH_MIN_BLOCKS 8
+#define RT_PATH_MIN_BLOCKS (1024 / RT_BLOCK)  // 32 resident warps per SM
 #endif
 #ifndef RT_PATH_REGEN_MIN
 #define RT_PATH_REGEN_MIN 8   // idle lanes that trigger a regeneration round (an all-idle warp always regenerates)

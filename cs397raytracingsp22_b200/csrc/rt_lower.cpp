@@ -931,7 +931,7 @@ int lower_scene(const std::vector<HostTexture>& textures, const std::vector<rt_m
     }
   }
   {
-    // the traversal stack (16 entries in shared memory + 48 in local memory) must hold the deepest path:
+    // the traversal stack (64 entries: RT_SMEM_STACK in shared memory, the rest in local memory) must hold the deepest path:
     // TLAS depth + one RESTORE marker + the deepest BLAS
     uint32_t deepest = 0;
     for (const HostObject& o : objects)
