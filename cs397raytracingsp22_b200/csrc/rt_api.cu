@@ -1047,7 +1047,10 @@ int rt_render_accum(rt_scene* s, const rt_camera* cam, const rt_render_opts* opt
   {
     bool worth = o.ray_sort == RT_RAYSORT_ON || (o.ray_sort == RT_RAYSORT_AUTO && inst_tris >= 16384ull);
     fr.sort_enabled = (worth && s->low.tlas_root != RT_ENTRY_NONE) ? 1u : 0u;
-    const int cells = 32;    // cells per axis of the TLAS box (measured: 8 / 16 / 32 / 64 -> 2253 / 2314 / 2348 / 2284 Msamples/s)
+#ifndef RT_SORT_CELLS
+#define RT_SORT_CELLS 32
+#endif
+    const int cells = RT_SORT_CELLS;    // cells per axis of the TLAS box (measured: 8 / 16 / 32 / 64 -> 2253 / 2314 / 2348 / 2284 Msamples/s)
     fr.sort_cells_m1 = (float)(cells - 1);
     fr.sort_use_octant = 2;  // direction class = octant + dominant axis (measured best of: none, octant, octant + axis)
     for (int k = 0; k < 3; ++k) {

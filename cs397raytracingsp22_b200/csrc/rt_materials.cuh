@@ -64,10 +64,10 @@ __device__ __forceinline__ uint32_t ray_sort_key(const rt_frame& fr, f3 o, f3 d)
     // 5 direction bits: octant + dominant axis (24 classes = the 6 cube faces x 4 quadrants), 13-bit cell hash
     float ax = fabsf(d.x), ay = fabsf(d.y), az = fabsf(d.z);
     uint32_t dom = (ax >= ay && ax >= az) ? 0u : (ay >= az ? 1u : 2u);
-    h = (h ^ (h >> 13)) & 0x1FFFu;
+    h = (h ^ (h >> 13)) & ((RT_SORT_BINS >> 5) - 1u);  // 13 bits with the default 2^18 bins
     return (h << 5) | (dom << 3) | oct;
   }
-  h = (h ^ (h >> 15)) & 0x7FFFu;
+  h = (h ^ (h >> 15)) & ((RT_SORT_BINS >> 3) - 1u);
   return (h << 3) | (fr.sort_use_octant ? oct : 0u);
 }
 

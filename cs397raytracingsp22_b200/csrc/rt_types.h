@@ -31,7 +31,9 @@
 #define RT_ENTRY_NONE 0xFFFFFFFFu
 #define RT_ENTRY_RESTORE 0xFFFFFFFEu
 #define RT_ENTRY_VOLRET 0xFFFFFFFDu  /* end of a boundary query of a mesh-bounded volume */
-#define RT_SORT_BINS 262144u  /* 15-bit spatial hash of the origin cell << 3 | direction octant */
+#ifndef RT_SORT_BINS
+#define RT_SORT_BINS 262144u  /* ray-sort key space: (spatial hash of the origin cell) << 5 | 5-bit direction class; a power of two >= 2^15 */
+#endif
 #define RT_MAX_LEAF_TRIS 8  /* fits the 4-bit count of a packed stack entry */
 
 enum rt_obj_kind { RT_OBJ_MESH = 0, RT_OBJ_SPHERE = 1, RT_OBJ_TRIANGLE = 2, RT_OBJ_PLANE = 3, RT_OBJ_VOLUME = 4,
