@@ -116,7 +116,8 @@ typedef struct rt_render_opts {
   uint32_t tile_size;     /* RT_SHARD_TILES: square tile edge in pixels (0 => 64)    */
   uint32_t sample_begin;  /* RT_SHARD_ALL/TILES: [begin,end) sample indices;         */
   uint32_t sample_end;    /*   both 0 => [0, aa_sample_count)                        */
-  uint32_t wavefront;     /* wavefront engine: paths in flight (0 => library default) */
+  uint32_t wavefront;     /* wavefront engine: paths in flight, 148 bytes of device state each (0 => library default:
+                             32 Mi paths = 5 GB, halved until the allocation succeeds) */
   uint32_t flags;         /* RT_OPT_*                                                */
   float point_light_pos[3]; /* Scene::point_light_pos, used by ShadingMode::Phong only (tracing.rs:216) */
   float ambient[3];         /* Scene::ambient, Phong only (tracing.rs:217)                              */
