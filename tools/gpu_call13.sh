@@ -4,8 +4,7 @@
 mkdir -p gpurun_out
 timeout 1500 python -m pytest tests -m gpu -x -q > gpurun_out/r2_pytest_gpu13.log 2>&1; echo "gpu suite rc=$?"
 tail -3 gpurun_out/r2_pytest_gpu13.log
-timeout 900 compute-sanitizer --tool memcheck --error-exitcode 9 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/r2_memcheck13.log 2>&1; echo "memcheck smoke rc=$?"
-tail -4 gpurun_out/r2_memcheck13.log
+# (a compute-sanitizer memcheck of smoke() stood here: the tool is closed on this GPU pool, gpurun refuses it)
 timeout 900 python bench.py --gpus 1 --steps 10 --warmup 3 > gpurun_out/bench_r2e_1gpu.json 2> gpurun_out/bench_r2e_1gpu.err; echo "bench N=1 rc=$?"
 python -c "
 import json; d=json.load(open('gpurun_out/bench_r2e_1gpu.json')); print({k: d[k] for k in ('value','ms_per_step','engine','gpu_launches')}, d['e2e']['value'], d['roofline_issue']['frac'], d['scene_build_s']); print({k:(round(v['value'],1),v['engine']) for k,v in d['configs'].items()}); print(d['cpu_baseline']['value'], d['cpu_baseline']['cores'])"
