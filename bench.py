@@ -328,9 +328,23 @@ def config_entry(args, name, rank, world, local, dev, barrier, flush, shard=None
     job = Job(args, name, rank, world, local, dev, shard=shard)
     big = job.W * job.H * job.spp > (1 << 32)                       # C5: one frame is tens of seconds on one GPU
     warm_spp = 64 if big else 0                                     # warm-up on a window of the sample indices
+    t0 = time.perf_counter()
     for _ in range(1 if big else 2):
         job.step(job.opts(sample_end=warm_spp), resolve_spp=warm_spp or None)
+    job.torch.cuda.synchronize()
     steps = 1 if big else 3
+    if not big:
+        # a frame of C1 takes 7 ms: three of them end before the clocks have come back up from the idle stretch of the
+        # previous configuration's CPU baseline.  Warm up for at least 0.3 s and time at least 0.5 s of frames.
+        per = max((time.perf_counter() - t0) / 2, 1e-4)
+        for _ in range(min(200, int(0.3 / per))):
+            job.step(job.opts())
+        steps = max(3, min(200, int(0.5 / per) + 1))
+        if world > 1:      # every rank must run the same number of steps
+            n = job.torch.tensor([steps], dtype=job.torch.int64, device=dev)
+            import torch.distributed as dist
+            dist.broadcast(n, src=0)
+            steps = int(n.item())
     ms, totals, stats, _ = timed_steps(job, steps, barrier, flush)
     entry = None
     if rank == 0:
