@@ -1,4 +1,4 @@
-// rt_config.cuh — compile-time knobs of the kernels (each one was measured, see profiles/r1_notes.md)
+// rt_config.cuh — compile-time knobs of the kernels (each one was measured, see profiles/r1_notes.md and r2_notes.md)
 #ifndef RT_CONFIG_CUH
 #define RT_CONFIG_CUH
 
@@ -55,7 +55,7 @@
 #ifndef RT_SORT_RANKED
 #define RT_SORT_RANKED 1
 #endif
-// Children per interior node come before this switch: with the binary tree, how a child pair is stored.
+// How a child pair of the binary tree is stored (RT_BVH4 above selects the tree).
 //   0: (min, max) per child, four 128-bit fetches per visit, slab test = 12 FFMA + 20 FMNMX(3)
 //   1: (centre, half extent) per child, four fetches, slab test = 18 FFMA + 8 FMNMX(3) (see slab_ch(), rt_traverse.cuh)
 //   2: packed pair - two centres with their links, six half extents as bf16 (rounded up) - THREE fetches per visit;
