@@ -10,10 +10,12 @@
 #define RT_BLOCK 256
 #endif
 #define RT_WARPS (RT_BLOCK / 32)
-// Traversal-stack entries per thread kept in shared memory; deeper entries live in local memory (L1).  16 entries
-// meant a 100 KB carve-out; 4 entries (64 KB) leave L1 36 KB more and are worth 0.4-0.6 % (profiles/r2_notes.md C7, C11).
+// Traversal-stack entries per thread kept in shared memory; the others live in local memory, i.e. in L1.  Measured
+// (profiles/r2_notes.md C7, C11): 16 entries mean a 100 KB carve-out; 4 entries (64 KB) are worth 0.4-0.6 % of that,
+// none at all (32 KB carve-out, 224 KB of L1; the stack's hot lines stay in L1 anyway) another 0.2 % on C4 and 0.5 %
+// on C5; 2 and 8 entries are slower than either neighbour.
 #ifndef RT_SMEM_STACK
-#define RT_SMEM_STACK 4
+#define RT_SMEM_STACK 0
 #endif
 #define RT_LOCAL_STACK (64 - RT_SMEM_STACK)  // overflow entries (local memory; 64 in all, the host checks depth <= 62)
 // RT_STREAM_HINTS: ray queue / hit record traffic uses the streaming (evict-first) cache operators so that it does

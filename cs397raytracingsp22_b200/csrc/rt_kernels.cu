@@ -95,7 +95,10 @@ __global__ void __launch_bounds__(RT_BLOCK) k_raygen(rt_frame fr, rt_ctrl* __res
 #define RT_REFILL_MIN 32
 #endif
 #ifndef RT_FETCH_CHUNK
-#define RT_FETCH_CHUNK 32  // measured: 32 -> 436 us, 64 -> 477 us, 256 -> 703 us per 2 M-ray iteration (load balance)
+// ray indices per claim (one atomic on one address).  Round 1, 2 Mi rays per launch: 32 -> 436 us, 64 -> 477 us,
+// 256 -> 703 us (load balance at the end of the launch).  With 32 Mi rays per launch the end of the launch matters
+// less and the atomic more: 32 / 64 / 128 -> C4 2723 / 2756 / 2688, C5 1811 / 1830 / 1821 Msamples/s (r2_notes.md C11).
+#define RT_FETCH_CHUNK 64
 #endif
 
 template <bool COUNT, bool VOLMESH>
